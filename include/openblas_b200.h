@@ -1,0 +1,210 @@
+/*
+ * openblas_b200.h -- C ABI of the B200-native GEMM library (libopenblas_b200.so).
+ *
+ * Every entry point in part 1 replaces, symbol for symbol, an entry point of the reference
+ * OpenBLAS 0.3.28.dev.  The file:line next to each one is the reference declaration it
+ * is bound against (paths relative to the reference tree).  A caller that was compiled
+ * against the reference's own cblas.h / common_interface.h links against this library
+ * unchanged: types, enum values, argument order and the xerbla_ protocol are identical.
+ *
+ * Part 2 holds the extension entry points (device-pointer / stream / multi-GPU panel
+ * helpers) used by bench.py, the SUMMA layer and the tests; they do not exist in the
+ * reference.
+ *
+ * There is NO CPU fallback behind any of these symbols: if no CUDA device is usable the
+ * call prints a diagnostic and aborts (b200_last_error() explains why).
+ */
+#ifndef OPENBLAS_B200_H
+#define OPENBLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types (openblas_config_template.h:36-45, common.h:263-279) ------------------- */
+#ifndef OPENBLAS_B200_NO_TYPES
+#ifdef OPENBLAS_USE64BITINT
+typedef int64_t blasint;
+#else
+typedef int blasint;
+#endif
+typedef uint16_t bfloat16;
+
+/* cblas.h:62-63 */
+typedef enum CBLAS_ORDER     {CblasRowMajor = 101, CblasColMajor = 102} CBLAS_ORDER;
+typedef enum CBLAS_TRANSPOSE {CblasNoTrans = 111, CblasTrans = 112, CblasConjTrans = 113,
+                              CblasConjNoTrans = 114} CBLAS_TRANSPOSE;
+typedef CBLAS_ORDER CBLAS_LAYOUT;
+#endif
+
+/* =====================================================================================
+ * Part 1 -- drop-in symbols
+ * ===================================================================================== */
+
+/* ---- CBLAS GEMM (cblas.h:298-307, cblas.h:444-445; body interface/gemm.c:294-651) --- */
+void cblas_sgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                 blasint M, blasint N, blasint K, float alpha, const float *A, blasint lda,
+                 const float *B, blasint ldb, float beta, float *C, blasint ldc);
+void cblas_dgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                 blasint M, blasint N, blasint K, double alpha, const double *A, blasint lda,
+                 const double *B, blasint ldb, double beta, double *C, blasint ldc);
+void cblas_cgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                 blasint M, blasint N, blasint K, const void *alpha, const void *A, blasint lda,
+                 const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_zgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                 blasint M, blasint N, blasint K, const void *alpha, const void *A, blasint lda,
+                 const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_sbgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                  blasint M, blasint N, blasint K, float alpha, const bfloat16 *A, blasint lda,
+                  const bfloat16 *B, blasint ldb, float beta, float *C, blasint ldc);
+
+/* ---- CBLAS GEMM3M (cblas.h:304-309; interface/gemm.c built with -DGEMM3M) ----------- */
+void cblas_cgemm3m(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                   blasint M, blasint N, blasint K, const void *alpha, const void *A, blasint lda,
+                   const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_zgemm3m(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                   blasint M, blasint N, blasint K, const void *alpha, const void *A, blasint lda,
+                   const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+
+/* ---- Fortran GEMM (common_interface.h:484-497; body interface/gemm.c:181-290) -------
+ * All arguments by reference, trans as one char of N/T/R/C in either case; no hidden
+ * string-length arguments are read. */
+void sgemm_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, float *alpha,
+            float *a, blasint *ldA, float *b, blasint *ldB, float *beta, float *c, blasint *ldC);
+void dgemm_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, double *alpha,
+            double *a, blasint *ldA, double *b, blasint *ldB, double *beta, double *c, blasint *ldC);
+void cgemm_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, float *alpha,
+            float *a, blasint *ldA, float *b, blasint *ldB, float *beta, float *c, blasint *ldC);
+void zgemm_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, double *alpha,
+            double *a, blasint *ldA, double *b, blasint *ldB, double *beta, double *c, blasint *ldC);
+void sbgemm_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, float *alpha,
+             bfloat16 *a, blasint *ldA, bfloat16 *b, blasint *ldB, float *beta, float *c,
+             blasint *ldC);
+void cgemm3m_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, float *alpha,
+              float *a, blasint *ldA, float *b, blasint *ldB, float *beta, float *c, blasint *ldC);
+void zgemm3m_(char *TRANSA, char *TRANSB, blasint *M, blasint *N, blasint *K, double *alpha,
+              double *a, blasint *ldA, double *b, blasint *ldB, double *beta, double *c,
+              blasint *ldC);
+
+/* ---- batched GEMM (cblas.h:419-430,446-447; body interface/gemm_batch.c:118-372) ---- */
+void cblas_sgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *TransA_array,
+                       const enum CBLAS_TRANSPOSE *TransB_array, const blasint *M_array,
+                       const blasint *N_array, const blasint *K_array, const float *alpha_array,
+                       const float **A_array, const blasint *lda_array, const float **B_array,
+                       const blasint *ldb_array, const float *beta_array, float **C_array,
+                       const blasint *ldc_array, blasint group_count, const blasint *group_size);
+void cblas_dgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *TransA_array,
+                       const enum CBLAS_TRANSPOSE *TransB_array, const blasint *M_array,
+                       const blasint *N_array, const blasint *K_array, const double *alpha_array,
+                       const double **A_array, const blasint *lda_array, const double **B_array,
+                       const blasint *ldb_array, const double *beta_array, double **C_array,
+                       const blasint *ldc_array, blasint group_count, const blasint *group_size);
+void cblas_cgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *TransA_array,
+                       const enum CBLAS_TRANSPOSE *TransB_array, const blasint *M_array,
+                       const blasint *N_array, const blasint *K_array, const void *alpha_array,
+                       const void **A_array, const blasint *lda_array, const void **B_array,
+                       const blasint *ldb_array, const void *beta_array, void **C_array,
+                       const blasint *ldc_array, blasint group_count, const blasint *group_size);
+void cblas_zgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *TransA_array,
+                       const enum CBLAS_TRANSPOSE *TransB_array, const blasint *M_array,
+                       const blasint *N_array, const blasint *K_array, const void *alpha_array,
+                       const void **A_array, const blasint *lda_array, const void **B_array,
+                       const blasint *ldb_array, const void *beta_array, void **C_array,
+                       const blasint *ldc_array, blasint group_count, const blasint *group_size);
+void cblas_sbgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *TransA_array,
+                        const enum CBLAS_TRANSPOSE *TransB_array, const blasint *M_array,
+                        const blasint *N_array, const blasint *K_array, const float *alpha_array,
+                        const bfloat16 **A_array, const blasint *lda_array,
+                        const bfloat16 **B_array, const blasint *ldb_array,
+                        const float *beta_array, float **C_array, const blasint *ldc_array,
+                        blasint group_count, const blasint *group_size);
+
+/* ---- bf16 conversion helpers callers of sbgemm need (cblas.h:433-440;
+ *      interface/tobf16.c, interface/bf16to.c; rounding rule kernel/x86_64/tobf16.c:46-96) */
+void cblas_sbstobf16(blasint n, const float *in, blasint incin, bfloat16 *out, blasint incout);
+void cblas_sbdtobf16(blasint n, const double *in, blasint incin, bfloat16 *out, blasint incout);
+void cblas_sbf16tos(blasint n, const bfloat16 *in, blasint incin, float *out, blasint incout);
+void cblas_dbf16tod(blasint n, const bfloat16 *in, blasint incin, double *out, blasint incout);
+void sbstobf16_(blasint *n, float *in, blasint *incin, bfloat16 *out, blasint *incout);
+void sbdtobf16_(blasint *n, double *in, blasint *incin, bfloat16 *out, blasint *incout);
+void sbf16tos_(blasint *n, bfloat16 *in, blasint *incin, float *out, blasint *incout);
+void dbf16tod_(blasint *n, bfloat16 *in, blasint *incin, double *out, blasint *incout);
+
+/* ---- error hook (driver/others/xerbla.c:56-73): weak, a caller's own xerbla_ wins ---- */
+int xerbla_(char *name, blasint *info, blasint len);
+
+/* ---- control API kept for callers (cblas.h:13-45).  Only exported by the stand-alone
+ *      library; the co-link build (libopenblas_b200_gemmonly.so) leaves them to
+ *      libopenblas.a (SURVEY 8(b) "Link recipe"). "threads" maps to nothing on a GPU:
+ *      set is accepted and remembered, get returns it. ------------------------------- */
+void  openblas_set_num_threads(int num_threads);
+void  goto_set_num_threads(int num_threads);
+int   openblas_get_num_threads(void);
+int   openblas_get_num_procs(void);
+char *openblas_get_config(void);
+char *openblas_get_corename(void);
+int   openblas_get_parallel(void);
+
+/* =====================================================================================
+ * Part 2 -- extensions (not in the reference)
+ * ===================================================================================== */
+
+/* precision codes used by the generic entry points below */
+enum b200_dtype { B200_S = 0, B200_D = 1, B200_C = 2, B200_Z = 3, B200_SB = 4 };
+/* op codes after normalisation (interface/gemm.c:245-269): N, T, R = conj, C = conj-trans */
+enum b200_trans { B200_N = 0, B200_T = 1, B200_R = 2, B200_C_ = 3 };
+
+/* kernel families; b200_set_kernel(B200_K_AUTO) restores the size-based choice */
+enum b200_kernel {
+  B200_K_AUTO = 0,
+  B200_K_GENERIC = 1, /* any shape/ld/alignment, all precisions: latency path          */
+  B200_K_FAST = 2     /* DMMA (d,z) / FFMA (s,c) / tcgen05 (sb) roofline kernels        */
+};
+
+/* Column-major C <- alpha*op(A)*op(B) + beta*C on DEVICE pointers, enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = the calling thread's library stream) without
+ * synchronising.  alpha/beta are HOST pointers to one FLOAT (s,d,sb) or two (c,z).
+ * Arguments are assumed valid (the BLAS entry points validate).  Returns 0 or a
+ * cudaError_t value. */
+int b200_gemm_async(int dtype, int transa, int transb, int64_t m, int64_t n, int64_t k,
+                    const void *alpha, const void *A, int64_t lda, const void *B, int64_t ldb,
+                    const void *beta, void *C, int64_t ldc, void *stream);
+
+/* Same operation, synchronous, pointers may each be host (pageable or pinned) or device.
+ * This is what every Part-1 entry point calls after validation. */
+int b200_gemm(int dtype, int transa, int transb, int64_t m, int64_t n, int64_t k,
+              const void *alpha, const void *A, int64_t lda, const void *B, int64_t ldb,
+              const void *beta, void *C, int64_t ldc);
+
+/* Force a kernel family for subsequent calls of this process (tests, profiling). */
+void b200_set_kernel(int kernel);
+int  b200_get_kernel(void);
+
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+uint64_t b200_launch_count(void);
+
+/* Name of the kernel the last b200_gemm*() of the calling thread dispatched to. */
+const char *b200_last_kernel(void);
+
+/* Last error text of the calling thread ("" if none). */
+const char *b200_last_error(void);
+
+/* Initialise eagerly on `device` (otherwise lazily on the current device at first call).
+ * Returns 0 on success. */
+int b200_init(int device);
+
+/* Pinned host memory helpers (what a caller should hand to the BLAS symbols to get
+ * full-rate DMA; pageable memory also works, through a staging ring). */
+void *b200_host_alloc(size_t bytes);
+void  b200_host_free(void *p);
+
+/* Version string, e.g. "openblas_b200 0.1 (sm_100a)". */
+const char *b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENBLAS_B200_H */

@@ -1,0 +1,66 @@
+/*
+ * gemm_common.cuh -- types shared by the device-side dispatcher and all GEMM kernels.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "shim.h"
+
+namespace b200 {
+
+/* A column-major problem with DEVICE pointers and scalars already read from the host.
+ * alpha/beta are carried as double pairs: every fp32 value is exactly representable, so the
+ * fp32 kernels narrow them back without rounding. */
+struct DeviceGemm {
+  int dtype;
+  int transa, transb;     /* 0 N, 1 T, 2 conj, 3 conj-trans */
+  int64_t m, n, k;
+  int64_t lda, ldb, ldc;
+  const void *a;
+  const void *b;
+  void *c;
+  double alpha_re, alpha_im;
+  double beta_re, beta_im;
+};
+
+/* per-precision element traits */
+template <int DT> struct Traits;
+template <> struct Traits<B200_S> {
+  using In = float; using Out = float; using Real = float;
+  static constexpr bool kComplex = false;
+};
+template <> struct Traits<B200_D> {
+  using In = double; using Out = double; using Real = double;
+  static constexpr bool kComplex = false;
+};
+template <> struct Traits<B200_C> {
+  using In = float2; using Out = float2; using Real = float;
+  static constexpr bool kComplex = true;
+};
+template <> struct Traits<B200_Z> {
+  using In = double2; using Out = double2; using Real = double;
+  static constexpr bool kComplex = true;
+};
+template <> struct Traits<B200_SB> {
+  using In = uint16_t; using Out = float; using Real = float;
+  static constexpr bool kComplex = false;
+};
+
+/* every kernel launch of the library goes through this counter (b200_launch_count) */
+void count_launch(const char *kernel_name);
+
+/* kernel family launchers: return cudaSuccess, or cudaErrorNotSupported when the family
+ * cannot take this problem (shape / alignment) and the dispatcher should fall through. */
+cudaError_t launch_generic(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_zgemm_dmma(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t stream);
+cudaError_t launch_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
+                           int64_t inc_out, cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace b200

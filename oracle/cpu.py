@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE -- ctypes access to the CPU checkers.
+
+  * `Oracle`     oracle/_build/liboracle.so, the plain-C restatement (gemm_oracle.c)
+  * `Reference`  oracle/_ref/<target>/libopenblas_ref.so, the unmodified reference compiled from
+                 its own sources (build_ref.py); the target is chosen from the host CPU's flags
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+Nothing under openblas_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+S, D, CX, Z, SB = 0, 1, 2, 3, 4
+DTYPE_NAMES = {S: "s", D: "d", CX: "c", Z: "z", SB: "sb"}
+NP_IN = {S: np.float32, D: np.float64, CX: np.complex64, Z: np.complex128, SB: np.uint16}
+NP_OUT = {S: np.float32, D: np.float64, CX: np.complex64, Z: np.complex128, SB: np.float32}
+TRANS_CHAR = "NTRC"
+CBLAS_TRANS = {0: 111, 1: 112, 2: 114, 3: 113}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def scalar_bytes(dtype, value):
+    """alpha/beta as the in-memory object the C ABI points at."""
+    if dtype in (CX, Z):
+        t = np.float32 if dtype == CX else np.float64
+        v = complex(value)
+        return np.array([v.real, v.imag], dtype=t)
+    t = np.float64 if dtype == D else np.float32
+    return np.array([value], dtype=t)
+
+
+def build_oracle():
+    so = os.path.join(HERE, "_build", "liboracle.so")
+    src = os.path.join(HERE, "gemm_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.oracle_gemm.restype = C.c_int
+        L.oracle_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_long, C.c_void_p,
+                                  C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                  C.c_long, C.c_long, C.c_long]
+        L.oracle_gemm_small.restype = C.c_int
+        L.oracle_gemm_small.argtypes = L.oracle_gemm.argtypes[:14]
+        L.oracle_mmch.restype = C.c_double
+        L.oracle_mmch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_long, C.c_void_p,
+                                  C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                  C.c_long, C.c_void_p, C.c_long]
+        L.oracle_componentwise_ratio.restype = C.c_double
+        L.oracle_componentwise_ratio.argtypes = L.oracle_mmch.argtypes + [C.c_void_p, C.c_long]
+        L.oracle_check_args.restype = C.c_int
+        L.oracle_check_args.argtypes = [C.c_int, C.c_int] + [C.c_long] * 6 + [C.c_int]
+        L.oracle_f32_to_bf16.restype = C.c_uint16
+        L.oracle_f32_to_bf16.argtypes = [C.c_float]
+        L.oracle_bf16_to_f32.restype = C.c_float
+        L.oracle_bf16_to_f32.argtypes = [C.c_uint16]
+        L.oracle_tobf16.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.oracle_bf16to.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+
+    def gemm(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, q=0, unroll_m=0, small=False):
+        """In-place on c (column-major storage, numpy arrays of the dtype's element type)."""
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        if small:
+            r = self.lib.oracle_gemm_small(dtype, ta, tb, m, n, k, _ptr(al), _ptr(a), lda, _ptr(b), ldb,
+                                           _ptr(be), _ptr(c), ldc)
+        else:
+            r = self.lib.oracle_gemm(dtype, ta, tb, m, n, k, _ptr(al), _ptr(a), lda, _ptr(b), ldb,
+                                     _ptr(be), _ptr(c), ldc, q, unroll_m)
+        assert r == 0
+        return c
+
+    def mmch(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc0, cc, ldcc):
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        return self.lib.oracle_mmch(dtype, ta, tb, m, n, k, _ptr(al), _ptr(a), lda, _ptr(b), ldb, _ptr(be),
+                                    _ptr(c0), ldc0, _ptr(cc), ldcc)
+
+    def ratio(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc0, x, ldx, y, ldy):
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        return self.lib.oracle_componentwise_ratio(dtype, ta, tb, m, n, k, _ptr(al), _ptr(a), lda, _ptr(b),
+                                                   ldb, _ptr(be), _ptr(c0), ldc0, _ptr(x), ldx, _ptr(y), ldy)
+
+    def check_args(self, ta, tb, m, n, k, lda, ldb, ldc, ok):
+        return self.lib.oracle_check_args(ta, tb, m, n, k, lda, ldb, ldc, ok)
+
+    def tobf16(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty(x.shape, dtype=np.uint16)
+        self.lib.oracle_tobf16(x.size, _ptr(x), 1, _ptr(out), 1)
+        return out
+
+    def bf16to(self, x):
+        x = np.ascontiguousarray(x, dtype=np.uint16)
+        out = np.empty(x.shape, dtype=np.float32)
+        self.lib.oracle_bf16to(x.size, _ptr(x), 1, _ptr(out), 1)
+        return out
+
+
+def cpu_flags():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def best_target(flags=None):
+    """Most capable reference build this host can execute (oracle/ref_recipe/*.recipe)."""
+    f = cpu_flags() if flags is None else flags
+    if {"amx_bf16", "amx_tile", "avx512_bf16", "avx512f", "avx512vl"} <= f:
+        return "sapphirerapids"
+    if {"avx512f", "avx512vl", "avx512dq", "avx512bw", "avx512cd"} <= f:
+        return "skylakex"
+    if {"avx2", "fma"} <= f:
+        return "haswell"
+    return "generic"
+
+
+def ref_path(target=None):
+    return os.path.join(HERE, "_ref", target or best_target(), "libopenblas_ref.so")
+
+
+def have_reference(target=None):
+    return os.path.exists(ref_path(target))
+
+
+class Reference:
+    """The reference library's own C ABI (cblas.h:298-307,444-445; common_interface.h:484-497)."""
+
+    def __init__(self, target=None):
+        self.target = target or best_target()
+        self.lib = C.CDLL(ref_path(self.target))
+        self.lib.openblas_get_config.restype = C.c_char_p
+        self.lib.openblas_get_corename.restype = C.c_char_p
+        self.lib.openblas_get_num_threads.restype = C.c_int
+
+    def config(self):
+        return self.lib.openblas_get_config().decode()
+
+    def set_threads(self, n):
+        self.lib.openblas_set_num_threads(int(n))
+
+    def threads(self):
+        return self.lib.openblas_get_num_threads()
+
+    def gemm(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """Column-major, through the Fortran symbol (what benchmark/gemm.c calls)."""
+        fn = getattr(self.lib, DTYPE_NAMES[dtype] + "gemm_")
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        i = lambda v: C.byref(C.c_int(int(v)))
+        fn(C.c_char_p(TRANS_CHAR[ta].encode()), C.c_char_p(TRANS_CHAR[tb].encode()), i(m), i(n), i(k),
+           _ptr(al), _ptr(a), i(lda), _ptr(b), i(ldb), _ptr(be), _ptr(c), i(ldc))
+        return c
