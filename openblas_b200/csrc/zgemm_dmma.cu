@@ -1,0 +1,207 @@
+/*
+ * zgemm_dmma.cu -- ZGEMM on the FP64 tensor pipe (DMMA.8x8x4).
+ *
+ * Stands in for the reference's zgemm_kernel_4x2_skylakex.c and its four conjugation variants
+ * (_n/_l/_r/_b built with -DNN/-DCN/-DNC/-DCC, kernel/Makefile.L3:877-916, chosen at
+ * level3.c:80-93) plus the zgemm_{i,o}{n,t}copy packing and zgemm_beta.  Complex operands stay
+ * INTERLEAVED (re,im) in global and shared memory -- there is no planar re-layout pass; a lane
+ * loads one complex number (16 bytes) per fragment element and the four real products of a
+ * complex multiply-accumulate become four DMMAs:
+ *
+ *     re += ar*br ;  re += (-ai')*bi' ;  im += ar*bi' ;  im += ai'*br
+ *
+ * where ai' / bi' carry the conjugation sign (op codes 2,3), applied to the fragment in
+ * registers, so all 16 op combinations share one of four kernels (stored orientation of A
+ * and B), 8*m*n*k real flops all on the DMMA pipe.
+ *
+ * CTA tile 64 (m) x 128 (n) complex, k step 8, 8 warps as 2 x 4 with 32 x 32 warp tiles,
+ * 4-stage cp.async ring.  As in dgemm_dmma.cu the MMA runs on the transposed tile so a lane
+ * owns two adjacent rows of a column of C.  Shared layouts in units of one complex (16 B):
+ * S[k][mn] with row stride = 2 mod 8 (66 / 130) or S[mn][k] with row stride 12 (= 4 mod 8):
+ * the 8 lanes of a quarter-warp (2 idx x 4 k) then hit 8 distinct 16-byte bank groups.
+ */
+#include "gemm_common.cuh"
+#include "async_copy.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int BM = 64, BN = 128, BK = 8;
+constexpr int STAGES = 4;
+constexpr int THREADS = 256;
+constexpr int WM = 32, WN = 32;
+constexpr int LDA_MN = BM + 2, LDB_MN = BN + 2, LD_K = BK + 4;
+constexpr int A_ELEMS = (BK * LDA_MN > BM * LD_K) ? BK * LDA_MN : BM * LD_K;   /* 768  */
+constexpr int B_ELEMS = (BK * LDB_MN > BN * LD_K) ? BK * LDB_MN : BN * LD_K;   /* 1536 */
+constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double2);  /* 144 KB */
+
+__device__ __forceinline__ double xor_sign(double x, int mask) {
+  return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+}
+
+/* (ROWS mn) x (8 k) complex tile, one 16-byte cp.async per element, zero fill outside. */
+template <bool MN_CONTIG, int ROWS, int LD_MN>
+__device__ __forceinline__ void load_tile(double2 *s, const double2 *__restrict__ g, int64_t ld, int64_t mn0,
+                                          int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
+#pragma unroll
+  for (int i = 0; i < ROWS * BK / THREADS; i++) {
+    int idx = tid + i * THREADS;
+    int k, mn;
+    if (MN_CONTIG) { k = idx / ROWS; mn = idx % ROWS; } else { k = idx % BK; mn = idx / BK; }
+    int64_t gk = k0 + k, gmn = mn0 + mn;
+    int bytes = (gk < k_end && gmn < mn_end) ? 16 : 0;
+    const double2 *src = bytes ? (MN_CONTIG ? g + gmn + gk * ld : g + gk + gmn * ld) : g;
+    cp_async16(MN_CONTIG ? s + k * LD_MN + mn : s + mn * LD_K + k, src, bytes);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+zgemm_dmma_kernel(DeviceGemm g) {
+  extern __shared__ __align__(16) double2 zsmem[];
+  const double2 *__restrict__ A = (const double2 *)g.a;
+  const double2 *__restrict__ B = (const double2 *)g.b;
+  double2 *__restrict__ C = (double2 *)g.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+  const int fi = lane >> 2, fk = lane & 3;
+  /* conjugation = flipping the sign bit of the imaginary part: done with integer XOR on the
+   * high word so that the FP64 pipe only ever sees DMMAs */
+  const int flip_a = (g.transa & 2) ? (int)0x80000000 : 0;
+  const int flip_b = (g.transb & 2) ? (int)0x80000000 : 0;
+
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
+  const int64_t tiles = tiles_m * tiles_n;
+  const int64_t ktiles = (g.k + BK - 1) / BK;
+
+  const int a_off = A_MN ? (fk * LDA_MN + wm + fi) : ((wm + fi) * LD_K + fk);
+  const int b_off = B_MN ? (fk * LDB_MN + wn + fi) : ((wn + fi) * LD_K + fk);
+  constexpr int A_MT = A_MN ? 8 : 8 * LD_K;
+  constexpr int B_NT = B_MN ? 8 : 8 * LD_K;
+  constexpr int A_K4 = A_MN ? 4 * LDA_MN : 4;
+  constexpr int B_K4 = B_MN ? 4 * LDB_MN : 4;
+
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    int64_t bm, bn;
+    banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+    const int64_t m0 = bm * BM, n0 = bn * BN;
+
+    double re[4][4][2], im[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) re[i][j][0] = re[i][j][1] = im[i][j][0] = im[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+      if (s < ktiles) {
+        double2 *sa = zsmem + s * STAGE_ELEMS, *sb = sa + A_ELEMS;
+        load_tile<A_MN, BM, LDA_MN>(sa, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, tid);
+        load_tile<B_MN, BN, LDB_MN>(sb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, tid);
+      }
+      cp_async_commit();
+    }
+
+    for (int64_t kt = 0; kt < ktiles; kt++) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+        int64_t nk = kt + STAGES - 1;
+        if (nk < ktiles) {
+          double2 *sa = zsmem + (nk % STAGES) * STAGE_ELEMS, *sb = sa + A_ELEMS;
+          load_tile<A_MN, BM, LDA_MN>(sa, A, g.lda, m0, nk * BK, g.m, g.k, tid);
+          load_tile<B_MN, BN, LDB_MN>(sb, B, g.ldb, n0, nk * BK, g.n, g.k, tid);
+        }
+        cp_async_commit();
+      }
+      const double2 *sa = zsmem + (kt % STAGES) * STAGE_ELEMS + a_off;
+      const double2 *sb = zsmem + (kt % STAGES) * STAGE_ELEMS + A_ELEMS + b_off;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; k4++) {
+        double ar[4], ai[4], nai[4], br[4], bi[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double2 v = sa[k4 * A_K4 + i * A_MT];
+          ar[i] = v.x; ai[i] = xor_sign(v.y, flip_a); nai[i] = xor_sign(ai[i], (int)0x80000000);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double2 v = sb[k4 * B_K4 + j * B_NT];
+          br[j] = v.x; bi[j] = xor_sign(v.y, flip_b);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            dmma884(re[i][j][0], re[i][j][1], br[j], ar[i]);
+            dmma884(im[i][j][0], im[i][j][1], bi[j], ar[i]);
+            dmma884(re[i][j][0], re[i][j][1], bi[j], nai[i]);
+            dmma884(im[i][j][0], im[i][j][1], br[j], ai[i]);
+          }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const double alr = g.alpha_re, ali = g.alpha_im, ber = g.beta_re, bei = g.beta_im;
+    const bool use_beta = !(ber == 0.0 && bei == 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t n = n0 + wn + 8 * j + fi;
+      if (n >= g.n) continue;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int64_t m = m0 + wm + 8 * i + 2 * fk + h;
+          if (m >= g.m) continue;
+          double2 *p = C + m + n * g.ldc;
+          double xr = re[i][j][h], xi = im[i][j][h];
+          double2 out;
+          out.x = alr * xr - ali * xi;
+          out.y = alr * xi + ali * xr;
+          if (use_beta) {
+            double2 old = *p;
+            out.x += ber * old.x - bei * old.y;
+            out.y += ber * old.y + bei * old.x;
+          }
+          *p = out;
+        }
+      }
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = zgemm_dmma_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t tiles = ((g.m + BM - 1) / BM) * ((g.n + BN - 1) / BN);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_zgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
+  if (g.dtype != B200_Z) return cudaErrorNotSupported;
+  /* one complex = one 16-byte cp.async: needs 16-byte aligned bases (any ld) */
+  if (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 15) return cudaErrorNotSupported;
+  const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  cudaError_t e;
+  if (a_mn && b_mn) e = launch_variant<true, true>(g, stream);
+  else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream);
+  else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream);
+  else e = launch_variant<false, false>(g, stream);
+  if (e == cudaSuccess) count_launch("zgemm_dmma_64x128x8");
+  return e;
+}
+
+}  // namespace b200

@@ -143,7 +143,9 @@ class Reference:
 
     def __init__(self, target=None):
         self.target = target or best_target()
-        self.lib = C.CDLL(ref_path(self.target))
+        # DEEPBIND: the reference must bind its internal calls (goto_set_num_threads, xerbla_, ...) to
+        # itself even when a library exporting the same names is already loaded in the process
+        self.lib = C.CDLL(ref_path(self.target), mode=os.RTLD_LOCAL | os.RTLD_DEEPBIND)
         self.lib.openblas_get_config.restype = C.c_char_p
         self.lib.openblas_get_corename.restype = C.c_char_p
         self.lib.openblas_get_num_threads.restype = C.c_int

@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol
+include/openblas_b200.h declares, and its argument validation / quick returns behave like
+interface/gemm.c -- exercised through the C ABI by a C harness that supplies its own xerbla_
+(the way ctest/c_xerbla.c does).  No compute call is made: none of this needs a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "openblas_b200.h")
+LIBDIR = os.path.join(ROOT, "openblas_b200", "lib")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([a-z][a-z0-9_]*)\s*\(", text)
+    skip = {"defined", "sizeof"}
+    return sorted({n for n in names if n not in skip and not n.startswith("openblas_dojob")})
+
+
+def test_header_declares_the_reference_symbols():
+    names = declared_symbols()
+    for must in ["cblas_sgemm", "cblas_dgemm", "cblas_cgemm", "cblas_zgemm", "cblas_sbgemm", "sgemm_", "dgemm_",
+                 "cgemm_", "zgemm_", "sbgemm_", "xerbla_", "cblas_dgemm_batch", "cblas_zgemm3m"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(ob):
+    lib = ctypes.CDLL(os.path.join(LIBDIR, "libopenblas_b200.so"))
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_gemmonly_library_leaves_control_symbols_to_libopenblas():
+    """SURVEY 8(b) link recipe: the co-link flavour must not define the control API."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(LIBDIR, "libopenblas_b200_gemmonly.so")],
+                                  text=True)
+    defined = {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+    assert "cblas_dgemm" in defined and "dgemm_" in defined
+    assert not ({"openblas_set_num_threads", "openblas_get_num_threads", "openblas_get_config"} & defined)
+    # xerbla_ is weak so a program's own definition wins
+    weak = [ln for ln in out.splitlines() if ln.endswith(" xerbla_")]
+    assert weak and weak[0].split()[-2] in ("W", "V")
+
+
+def test_no_oracle_or_cpu_blas_linked_into_the_product():
+    out = subprocess.check_output(["ldd", os.path.join(LIBDIR, "libopenblas_b200.so")], text=True)
+    assert "oracle" not in out and "openblas_ref" not in out and "libopenblas.so" not in out
+    syms = subprocess.check_output(["nm", "-D", os.path.join(LIBDIR, "libopenblas_b200.so")], text=True)
+    assert "oracle_gemm" not in syms
+
+
+def test_control_api(ob):
+    lib = ob.lib()
+    lib.openblas_set_num_threads(5)
+    assert lib.openblas_get_num_threads() == 5
+    assert lib.openblas_get_num_procs() >= 1
+    assert b"B200" in lib.openblas_get_corename()
+    assert lib.openblas_get_parallel() in (0, 1, 2)
+    assert b"sm_100a" in lib.openblas_get_config()
+
+
+def test_error_exits_and_quick_returns_through_c_abi(tmp_path, ob):
+    exe = tmp_path / "errexit"
+    subprocess.check_call(["gcc", "-O1", "-Wall", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", "errexit.c"),
+                           "-o", str(exe), f"-L{LIBDIR}", "-lopenblas_b200", f"-Wl,-rpath,{LIBDIR}"])
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    assert "ERROR EXITS PASSED" in r.stdout
+
+
+def test_default_xerbla_prints_reference_message(ob, capfd):
+    import numpy as np
+    a = np.zeros(4)
+    ob.cblas.dgemm(ob.cblas.ColMajor, ob.cblas.NoTrans, ob.cblas.NoTrans, 1, -1, 1, 1.0, a, 1, a, 1, 0.0, a, 1)
+    # driver/others/xerbla.c:49-53 message format
+    ctypes.CDLL(None).fflush(None)
+    out = capfd.readouterr().out
+    assert " ** On entry to DGEMM  parameter number  4 had an illegal value" in out

@@ -1,0 +1,44 @@
+"""The reference's own acceptance programs, UNMODIFIED, linked against libopenblas_b200.so as a
+drop-in (oracle/build_ref.py compiles ctest/c_?blat3c.c, c_?blas3.c, c_?3chke.c, c_xerbla.c from
+/root/reference and links them first against our library): 27 783 cblas_?gemm calls per layout
+for s/d/z (17 496 for c) plus the error-exit checks, each judged by the reference's DMMCH.
+Inputs: the reference's ?in3 files with the non-GEMM routines switched off
+(tests/golden/ctest_in3, written by tests/golden/make_golden.py)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CTEST = os.path.join(ROOT, "oracle", "_ref", "ctest")
+
+
+@pytest.mark.parametrize("p", list("sdcz"))
+def test_ctest_level3_gemm(p):
+    exe = os.path.join(CTEST, f"x{p}cblat3")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ctest not built (needs /root/reference at build time)")
+    with open(os.path.join(ROOT, "tests", "golden", "ctest_in3", f"{p}in3")) as f:
+        r = subprocess.run([exe], stdin=f, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    out = r.stdout
+    print(out[-3000:])
+    assert r.returncode == 0, out[-2000:]
+    assert "FATAL" not in out and "FAIL" not in out.replace("FAILURES", ""), out[-2000:]
+    import re
+    assert len(re.findall(rf"cblas_{p}gemm\s+PASSED THE TESTS OF ERROR-EXITS", out)) == 1, out[-2000:]
+    calls = 17496 if p == "c" else 27783
+    assert re.search(rf"cblas_{p}gemm\s+PASSED THE COLUMN-MAJOR COMPUTATIONAL TESTS \(\s*{calls} CALLS\)", out), out[-2000:]
+    assert re.search(rf"cblas_{p}gemm\s+PASSED THE ROW-MAJOR\s+COMPUTATIONAL TESTS \(\s*{calls} CALLS\)", out), out[-2000:]
+
+
+def test_compare_sgemm_sbgemm():
+    """test/compare_sgemm_sbgemm.c, SBGEMM half (the SBGEMV half is outside the GEMM path; the
+    link-time stub ends the program successfully once the SBGEMM half has passed)."""
+    exe = os.path.join(CTEST, "test_sbgemm")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ctest not built")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert "FATAL ERROR SBGEMM" not in r.stdout, r.stdout[-1000:]
+    assert r.returncode == 0, r.stdout[-1000:]
+    assert "SBGEMM half PASSED" in r.stdout

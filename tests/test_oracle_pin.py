@@ -1,0 +1,170 @@
+"""CPU tests that PIN the oracle (oracle/gemm_oracle.c) to the reference:
+
+  1. bit-for-bit against golden vectors the reference's GENERIC-target build produced
+     (tests/golden/gemm_golden.npz, written by tests/golden/make_golden.py)
+  2. bit-for-bit against oracle/_ref/generic and within the summation-order bound against the
+     best SIMD build, live, when oracle/_ref is present (authoring container and GPU box)
+  3. the DMMCH-style checker is self-checked with exact integer data, as the reference does
+     (ctest/c_dblat3.f:211-272)
+  4. bf16 conversions against vectors from the reference's sbstobf16_/sbf16tos_
+  5. argument validation against the expectations of the reference's error-exit test
+     (ctest/c_d3chke.c:45-272)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+from helpers import ALL_DTYPES, C_BOUND, NAMES, THRESH, alpha_beta, ntrans, problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_oracle_matches_reference_golden_bitwise(oracle, golden):
+    meta = golden["meta"]
+    assert len(meta) == 88
+    for idx, row in enumerate(meta):
+        dtype, ta, tb, m, n, k, lda, ldb, ldc = (int(v) for v in row[:9])
+        alpha = complex(row[9], row[10]) if dtype in (cpu.CX, cpu.Z) else row[9]
+        beta = complex(row[11], row[12]) if dtype in (cpu.CX, cpu.Z) else row[11]
+        c = golden[f"c0_{idx}"].copy()
+        oracle.gemm(dtype, ta, tb, m, n, k, alpha, golden[f"a{idx}"], lda, golden[f"b{idx}"], ldb, beta, c, ldc)
+        want = golden[f"c{idx}"]
+        assert np.array_equal(c.view(np.uint8), want.view(np.uint8)), (idx, NAMES[dtype], ta, tb, m, n, k)
+        # padding rows of C are never written
+        assert np.all(c[:, m:].real == -1e10)
+
+
+@pytest.mark.skipif(not cpu.have_reference("generic"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_oracle_vs_live_reference(oracle, dtype):
+    gen = cpu.Reference("generic")
+    gen.set_threads(1)
+    best = cpu.Reference()
+    rng = np.random.default_rng(100 + dtype)
+    alphas, betas = alpha_beta(dtype)
+    worst = 0.0
+    for (m, n, k) in [(3, 2, 1), (33, 17, 250), (64, 48, 519), (130, 70, 300)]:
+        for ta in range(ntrans(dtype)):
+            for tb in range(ntrans(dtype)):
+                alpha, beta = alphas[(m + ta) % 3], betas[(n + tb) % 3]
+                a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k)
+                c1, c2, c3 = c0.copy(), c0.copy(), c0.copy()
+                oracle.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c1, ldc)
+                gen.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c2, ldc)
+                best.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c3, ldc)
+                assert np.array_equal(c1.view(np.uint8), c2.view(np.uint8)), (NAMES[dtype], m, n, k, ta, tb)
+                r = oracle.ratio(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, c1, ldc, c3, ldc)
+                worst = max(worst, r)
+                # and both pass the reference's own acceptance test
+                assert oracle.mmch(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, c3, ldc) < THRESH
+    assert worst <= C_BOUND, worst
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_small_matrix_restatement_agrees(oracle, dtype):
+    """interface/gemm.c:551-571 small-matrix kernels vs the blocked driver: same result to
+    rounding order."""
+    rng = np.random.default_rng(7)
+    for ta in range(ntrans(dtype)):
+        for tb in range(ntrans(dtype)):
+            m, n, k = 9, 7, 35
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k)
+            alpha, beta = alpha_beta(dtype)[0][2], alpha_beta(dtype)[1][2]
+            c1, c2 = c0.copy(), c0.copy()
+            oracle.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c1, ldc)
+            oracle.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c2, ldc, small=True)
+            assert oracle.ratio(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, c1, ldc, c2, ldc) <= C_BOUND
+            assert np.all(c2[:, m:].real == -1e10)
+
+
+def test_mmch_selfcheck_exact_integers(oracle):
+    """c_dblat3.f:211-272: with small integer data the product is exact, so the checker must
+    report 0 for the right answer and a large ratio for a wrong one."""
+    n = 8
+    for dtype in (cpu.S, cpu.D):
+        t = cpu.NP_IN[dtype]
+        ab = np.array([[max(i - j + 1, 0) for i in range(n)] for j in range(n)], dtype=t)  # (cols, ld)
+        bb = np.array([[j * 3 + 1 if i == 0 else 3 for i in range(n)] for j in range(n)], dtype=t)
+        want = (ab.T.astype(np.float64) @ bb.T.astype(np.float64)).T.astype(t)
+        c0 = np.zeros((n, n), dtype=t)
+        assert oracle.mmch(dtype, 0, 0, n, n, n, 1.0, ab, n, bb, n, 0.0, c0, n, np.ascontiguousarray(want), n) == 0.0
+        wrong = np.ascontiguousarray(want + 1)
+        assert oracle.mmch(dtype, 0, 0, n, n, n, 1.0, ab, n, bb, n, 0.0, c0, n, wrong, n) > 1e3
+        got = c0.copy()
+        oracle.gemm(dtype, 0, 0, n, n, n, 1.0, ab, n, bb, n, 0.0, got, n)
+        assert np.array_equal(got, want)
+
+
+def test_bf16_conversion_golden(oracle):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bf16_golden.npz"))
+    got = oracle.tobf16(g["x"])
+    assert np.array_equal(got, g["bf16"])
+    back = oracle.bf16to(g["bf16"])
+    assert np.array_equal(back.view(np.uint32), g["back"].view(np.uint32))
+
+
+def test_beta_zero_never_reads_c(oracle):
+    """kernel/generic/gemm_beta.c:52-71: NaN/Inf in C must not survive beta == 0."""
+    rng = np.random.default_rng(3)
+    for dtype in ALL_DTYPES:
+        a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 0, 0, 5, 4, 3)
+        c0[:, :5] = np.nan
+        c = c0.copy()
+        oracle.gemm(dtype, 0, 0, 5, 4, 3, 1.0, a, lda, b, ldb, 0.0, c, ldc)
+        assert np.all(np.isfinite(c[:4, :5]))
+        # alpha == 0: A and B are not read (level3.c:252-259) -> NaN there cannot leak
+        a2 = a.copy()
+        if dtype != cpu.SB:
+            a2[:] = np.nan
+        else:
+            a2[:] = 0x7fc0
+        c = operand_finite(c0)
+        oracle.gemm(dtype, 0, 0, 5, 4, 3, 0.0, a2, lda, b, ldb, 1.3, c, ldc)
+        assert np.all(np.isfinite(c[:4, :5]))
+
+
+def operand_finite(c0):
+    c = c0.copy()
+    c[np.isnan(c)] = 0.25
+    return c
+
+
+# (order-independent part of) ctest/c_d3chke.c:45-272: each tuple is a bad call and the info
+# xerbla_ must receive; trans codes after decoding, column-major
+ERROR_EXITS = [
+    # transa transb  m  n  k lda ldb ldc  info
+    (-1, 0, 0, 0, 0, 1, 1, 1, 1),
+    (-1, 1, 0, 0, 0, 1, 1, 1, 1),
+    (0, -1, 0, 0, 0, 1, 1, 1, 2),
+    (1, -1, 0, 0, 0, 1, 1, 1, 2),
+    (0, 0, -1, 0, 0, 1, 1, 1, 3),
+    (0, 1, -1, 0, 0, 1, 1, 1, 3),
+    (1, 0, -1, 0, 0, 1, 1, 1, 3),
+    (1, 1, -1, 0, 0, 1, 1, 1, 3),
+    (0, 0, 0, -1, 0, 1, 1, 1, 4),
+    (1, 1, 0, -1, 0, 1, 1, 1, 4),
+    (0, 0, 0, 0, -1, 1, 1, 1, 5),
+    (1, 0, 0, 0, -1, 1, 1, 1, 5),
+    (0, 0, 2, 0, 0, 1, 1, 2, 8),
+    (0, 1, 2, 0, 0, 1, 1, 2, 8),
+    (1, 0, 0, 0, 2, 1, 2, 1, 8),
+    (1, 1, 0, 0, 2, 1, 1, 1, 8),
+    (0, 0, 0, 0, 2, 1, 1, 1, 10),
+    (1, 0, 0, 0, 2, 2, 1, 1, 10),
+    (0, 1, 0, 2, 0, 1, 1, 1, 10),
+    (1, 1, 0, 2, 0, 1, 1, 1, 10),
+    (0, 0, 2, 0, 0, 2, 1, 1, 13),
+    (0, 1, 2, 0, 0, 2, 1, 1, 13),
+    (1, 0, 2, 0, 0, 1, 1, 1, 13),
+    (1, 1, 2, 0, 0, 1, 1, 1, 13),
+]
+
+
+def test_argument_validation_table(oracle):
+    for ta, tb, m, n, k, lda, ldb, ldc, want in ERROR_EXITS:
+        assert oracle.check_args(ta, tb, m, n, k, lda, ldb, ldc, -1) == want
+    assert oracle.check_args(0, 0, 3, 4, 5, 3, 5, 3, -1) == -1
+    # OpenBLAS accepts ldc == m == 0 (weaker than Netlib's max(1,m)): interface/gemm.c:276
+    assert oracle.check_args(0, 0, 0, 4, 5, 1, 5, 0, 0) == 0

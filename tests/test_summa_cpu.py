@@ -1,0 +1,102 @@
+"""CPU tests of the multi-GPU layer's HOST logic (openblas_b200/summa.py) with 2 processes on the
+gloo backend: grid shape, block-cyclic ownership maps, the panel schedule, and a full SUMMA sweep
+whose local product is done by the CPU oracle (test-only injection; on GPUs it is the library's
+b200_gemm_async).  The distributed result must equal the single-process oracle result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openblas_b200 import summa  # noqa: E402
+
+
+def test_grid_shapes_follow_divide_rule():
+    # gemm_thread_mn.c:43-61 divide_rule: squarest grid, more columns than rows
+    assert summa.grid_shape(1) == (1, 1)
+    assert summa.grid_shape(2) == (1, 2)
+    assert summa.grid_shape(4) == (2, 2)
+    assert summa.grid_shape(8) == (2, 4)
+    assert summa.grid_shape(6) == (2, 3)
+
+
+def test_block_cyclic_ownership_partitions_every_index():
+    for n, nb, p in [(10, 3, 2), (32768, 2048, 4), (17, 5, 3), (4, 8, 2), (0, 4, 2)]:
+        seen = []
+        for ip in range(p):
+            idx = summa.local_index_map(n, nb, ip, p)
+            assert len(idx) == summa.numroc(n, nb, ip, p)
+            seen += idx
+        assert sorted(seen) == list(range(n))
+
+
+def test_panel_schedule_has_one_owner_per_panel():
+    k, nb, P, Q = 23, 4, 2, 3
+    steps = summa.panel_schedule(k, nb, P, Q)
+    assert sum(w for _, w, *_ in steps) == k
+    for k0, w, qa, ca, pb, rb in steps:
+        a_cols = summa.local_index_map(k, nb, qa, Q)
+        b_rows = summa.local_index_map(k, nb, pb, P)
+        assert a_cols[ca:ca + w] == list(range(k0, k0 + w))
+        assert b_rows[rb:rb + w] == list(range(k0, k0 + w))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, m, n, k, nb, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import cpu
+    oracle = cpu.Oracle()
+    rng = np.random.default_rng(42)          # same global matrices on every rank
+    A = torch.from_numpy(rng.random((k, m)) - 0.5)   # (cols, rows) storage of m x k
+    B = torch.from_numpy(rng.random((n, k)) - 0.5)
+    C = torch.from_numpy(rng.random((n, m)) - 0.5)
+    grid = summa.make_grid(world, rank)
+    a_loc = summa.scatter_from_global(A, nb, grid, rows_by="p", cols_by="q")
+    b_loc = summa.scatter_from_global(B, nb, grid, rows_by="p", cols_by="q")
+    c_loc = summa.scatter_from_global(C, nb, grid, rows_by="p", cols_by="q")
+
+    def local_gemm(mm, nn, kk, alpha, a, lda, b, ldb, beta, c, ldc, stream):
+        oracle.gemm(cpu.D, 0, 0, mm, nn, kk, alpha, a.numpy(), lda, b.numpy(), ldb, beta, c.numpy(), ldc)
+
+    sm = summa.Summa(grid, m, n, k, nb, torch.float64, "cpu", local_gemm)
+    assert (sm.m_loc, sm.n_loc) == (c_loc.shape[1], c_loc.shape[0])
+    sm.run(0.7, a_loc, b_loc, 1.3, c_loc)
+    want = C.numpy().copy()
+    oracle.gemm(cpu.D, 0, 0, m, n, k, 0.7, A.numpy(), m, B.numpy(), k, 1.3, want, m)
+    ri = summa.local_index_map(m, nb, grid.p, grid.P)
+    ci = summa.local_index_map(n, nb, grid.q, grid.Q)
+    ref_loc = want[np.ix_(ci, ri)]
+    err = float(np.max(np.abs(ref_loc - c_loc.numpy()))) if ref_loc.size else 0.0
+    out[rank] = (err, sm.launches, len(sm.steps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(37, 29, 23, 4), (16, 16, 16, 8), (5, 40, 9, 3)])
+def test_summa_two_ranks_gloo_matches_oracle(shape):
+    m, n, k, nb = shape
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, m, n, k, nb, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        err, launches, steps = out[rank]
+        assert err < 1e-12, (rank, err)
+        assert launches == steps == (k + nb - 1) // nb
