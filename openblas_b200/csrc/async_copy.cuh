@@ -1,6 +1,7 @@
 /* async_copy.cuh -- cp.async (LDGSTS) helpers shared by the cp.async-fed kernels. */
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 
 namespace b200 {
 
@@ -41,5 +42,147 @@ __device__ __forceinline__ void banded_tile_coords(int64_t t, int64_t tiles_m, i
   bm = band * BAND + r % band_rows;
   bn = r / band_rows;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * TileLoader: a thread's share of the cp.async traffic for one (ROWS mn) x (BK k) operand tile,
+ * with ALL address arithmetic hoisted out of the k loop.  (First version recomputed 64-bit
+ * addresses and bounds per 16-byte chunk per k tile: ncu showed ~2 integer instructions per DMMA
+ * and IMADs competing with FFMA for the FMA pipe.)  Per k tile a thread now does, per chunk, one
+ * pointer add and one LDGSTS; bounds in the mn direction are fixed per C tile, bounds in the k
+ * direction only matter in the last k tile (issue_tail).
+ *
+ *   MN_CONTIG  element (mn,k) at g[mn + k*ld]  -> shared S[k][mn], row stride LD elements
+ *   !MN_CONTIG element (mn,k) at g[k + mn*ld]  -> shared S[mn][k], row stride LD elements
+ * ES = element bytes (4, 8, 16); chunks are 16 bytes (VE = 16/ES elements).  Requires 16-byte
+ * aligned base and ld*ES % 16 == 0 (callers fall back to an element-wise loader otherwise). */
+template <bool MN_CONTIG, int ES, int ROWS, int BK, int LD, int THREADS>
+struct TileLoader {
+  static constexpr int VE = 16 / ES;
+  static constexpr int CPR = MN_CONTIG ? ROWS / VE : BK / VE;   /* chunks per contiguous run */
+  static constexpr int STEP = THREADS / CPR;                    /* k rows (or mn rows) between a thread's chunks */
+  static constexpr int N = (ROWS * BK / VE) / THREADS;          /* chunks per thread per tile */
+  static constexpr int DST_STEP = STEP * LD * ES;               /* bytes between chunks in shared memory */
+  static_assert(THREADS % CPR == 0 && (ROWS * BK / VE) % THREADS == 0, "tile does not divide among threads");
+
+  const char *src;     /* this thread's chunk 0 of the CURRENT k tile */
+  const char *safe;    /* any mapped address, used with src-size 0 */
+  int64_t src_step;    /* bytes between a thread's consecutive chunks in global memory */
+  int64_t k_adv;       /* bytes per k tile */
+  uint32_t dst;        /* byte offset of chunk 0 inside the operand's shared tile */
+  int edge;            /* MN_CONTIG: valid bytes of every chunk (mn edge). else: number of valid chunks */
+  int krow;            /* MN_CONTIG: k row of chunk 0.  else: first k element of the chunks */
+
+  __device__ __forceinline__ void init(const void *g, int64_t ld, int64_t mn0, int64_t mn_end, int tid) {
+    safe = (const char *)g;
+    const int run = tid % CPR, row = tid / CPR;
+    if (MN_CONTIG) {
+      const int64_t mn = mn0 + (int64_t)run * VE;
+      int64_t left = mn_end - mn;
+      edge = left >= VE ? 16 : (left > 0 ? (int)left * ES : 0);
+      src = (const char *)g + (mn + (int64_t)row * ld) * ES;
+      src_step = (int64_t)STEP * ld * ES;
+      k_adv = (int64_t)BK * ld * ES;
+      dst = (uint32_t)((row * LD + run * VE) * ES);
+      krow = row;
+    } else {
+      const int64_t mn = mn0 + row;
+      int64_t left = mn_end - mn;                                /* rows from mine to the edge */
+      int64_t nv = left > 0 ? (left + STEP - 1) / STEP : 0;
+      edge = nv > N ? N : (int)nv;
+      src = (const char *)g + ((int64_t)run * VE + mn * ld) * ES;
+      src_step = (int64_t)STEP * ld * ES;
+      k_adv = (int64_t)BK * ES;
+      dst = (uint32_t)((row * LD + run * VE) * ES);
+      krow = run * VE;
+    }
+  }
+  /* full k tile */
+  __device__ __forceinline__ void issue(uint32_t smem_tile) const {
+    const char *p = src;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const int bytes = MN_CONTIG ? edge : (i < edge ? 16 : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_tile + dst + i * DST_STEP),
+                   "l"(bytes ? p : safe), "r"(bytes) : "memory");
+      p += src_step;
+    }
+  }
+  /* last, partial k tile: k_left (< BK) valid k */
+  __device__ __forceinline__ void issue_tail(uint32_t smem_tile, int k_left) const {
+    const char *p = src;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      int bytes;
+      if (MN_CONTIG) bytes = (krow + i * STEP < k_left) ? edge : 0;
+      else {
+        int kl = k_left - krow;
+        bytes = (i < edge && kl > 0) ? (kl >= VE ? 16 : kl * ES) : 0;
+      }
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_tile + dst + i * DST_STEP),
+                   "l"(bytes ? p : safe), "r"(bytes) : "memory");
+      p += src_step;
+    }
+  }
+  __device__ __forceinline__ void advance() { src += k_adv; }
+  /* step back to k tile 0 of the same C tile is never needed: init() is called per C tile */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * KStager: the register-staged, TRANSPOSING path of the FFMA kernels for an operand stored
+ * k-contiguous (element (mn,k) at g[k + mn*ld]) whose shared-memory image must be S[k][mn].
+ * fetch() issues the thread's 16-byte global loads for the NEXT k tile before the FMA block,
+ * store() scatters them into S[k][mn] after it.  Addresses are hoisted like in TileLoader.
+ * T = float (VE = 4) or float2 (VE = 2). */
+template <class T, int ROWS, int BK, int LDS, int THREADS>
+struct KStager {
+  static constexpr int ES = sizeof(T), VE = 16 / ES;
+  static constexpr int CPR = BK / VE;
+  static constexpr int STEP = THREADS / CPR;
+  static constexpr int N = (ROWS * BK / VE) / THREADS;
+  static_assert(THREADS % CPR == 0 && (ROWS * BK / VE) % THREADS == 0, "tile does not divide among threads");
+  const char *src;
+  int64_t src_step, ld_bytes;
+  int nvalid, kq, row;
+  bool vec;
+
+  __device__ __forceinline__ void init(const void *g, int64_t ld, int64_t mn0, int64_t mn_end, bool aligned, int tid) {
+    const int run = tid % CPR;
+    row = tid / CPR;
+    kq = run * VE;
+    const int64_t mn = mn0 + row, left = mn_end - mn;
+    int64_t nv = left > 0 ? (left + STEP - 1) / STEP : 0;
+    nvalid = nv > N ? N : (int)nv;
+    src = (const char *)g + ((int64_t)kq + mn * ld) * ES;
+    src_step = (int64_t)STEP * ld * ES;
+    vec = aligned;
+  }
+  __device__ __forceinline__ void fetch(T (&r)[N * VE], int k_left /* >= BK for a full tile */) const {
+    const char *p = src;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (i < nvalid && vec && kq + VE <= k_left) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int x = 0; x < VE; x++) r[i * VE + x] = e[x];
+      } else {
+#pragma unroll
+        for (int x = 0; x < VE; x++) {
+          T z; memset(&z, 0, sizeof z);
+          r[i * VE + x] = (i < nvalid && kq + x < k_left) ? reinterpret_cast<const T *>(p)[x] : z;
+        }
+      }
+      p += src_step;
+    }
+  }
+  __device__ __forceinline__ void store(T *s, const T (&r)[N * VE]) const {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int x = 0; x < VE; x++) s[(kq + x) * LDS + row + i * STEP] = r[i * VE + x];
+  }
+  __device__ __forceinline__ void advance() { src += (int64_t)BK * ES; }
+};
 
 }  // namespace b200

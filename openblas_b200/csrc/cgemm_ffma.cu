@@ -44,57 +44,16 @@ __device__ __forceinline__ void ffma2(u64 &c, u64 a, u64 b) {
   asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
 }
 
-__device__ __forceinline__ void load_mn_async(float2 *s, const float2 *__restrict__ g, int64_t ld, int64_t mn0,
-                                              int64_t k0, int64_t mn_end, int64_t k_end, bool vec, int tid) {
-  if (vec) {
-#pragma unroll
-    for (int i = 0; i < (BM / 2) * BK / THREADS; i++) {   /* 2 */
-      int idx = tid + i * THREADS;
-      int k = idx / (BM / 2), mn = (idx % (BM / 2)) * 2;
-      int64_t gk = k0 + k, gmn = mn0 + mn;
-      int64_t left = (gk < k_end) ? (mn_end - gmn) : 0;
-      int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-      const float2 *src = bytes ? g + gmn + gk * ld : g;
-      cp_async16(s + k * LDS + mn, src, bytes);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < BM * BK / THREADS; i++) {         /* 4 */
-      int idx = tid + i * THREADS;
-      int k = idx / BM, mn = idx % BM;
-      int64_t gk = k0 + k, gmn = mn0 + mn;
-      int bytes = (gk < k_end && gmn < mn_end) ? 8 : 0;
-      const float2 *src = bytes ? g + gmn + gk * ld : g;
-      cp_async8(s + k * LDS + mn, src, bytes);
-    }
-  }
-}
-
-/* k-contiguous operand: element (mn,k) at g[k + mn*ld]; a thread owns two (mn, 2 k) pairs */
-__device__ __forceinline__ void fetch_k(float2 (&r)[4], const float2 *__restrict__ g, int64_t ld, int64_t mn0,
-                                        int64_t k0, int64_t mn_end, int64_t k_end, bool vec, int tid) {
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
+/* Element-wise fallback for an mn-contiguous operand that is not 16-byte aligned. */
+__device__ __noinline__ void load_mn_unaligned(float2 *s, const float2 *__restrict__ g, int64_t ld, int64_t mn0,
+                                               int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
+  for (int i = 0; i < BM * BK / THREADS; i++) {
     int idx = tid + i * THREADS;
-    int kq = (idx % 8) * 2, mn = idx / 8;
-    int64_t gk = k0 + kq, gmn = mn0 + mn;
-    if (gmn < mn_end && gk + 1 < k_end && vec) {
-      float4 v = *reinterpret_cast<const float4 *>(g + gk + gmn * ld);
-      r[2 * i] = make_float2(v.x, v.y); r[2 * i + 1] = make_float2(v.z, v.w);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 2; e++)
-        r[2 * i + e] = (gmn < mn_end && gk + e < k_end) ? g[gk + e + gmn * ld] : make_float2(0.f, 0.f);
-    }
-  }
-}
-__device__ __forceinline__ void store_k(float2 *s, const float2 (&r)[4], int tid) {
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    int idx = tid + i * THREADS;
-    int kq = (idx % 8) * 2, mn = idx / 8;
-#pragma unroll
-    for (int e = 0; e < 2; e++) s[(kq + e) * LDS + mn] = r[2 * i + e];
+    int k = idx / BM, mn = idx % BM;
+    int64_t gk = k0 + k, gmn = mn0 + mn;
+    int bytes = (gk < k_end && gmn < mn_end) ? 8 : 0;
+    const float2 *src = bytes ? g + gmn + gk * ld : g;
+    cp_async8(s + k * LDS + mn, src, bytes);
   }
 }
 
@@ -114,6 +73,7 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
   const int64_t tiles = tiles_m * tiles_n;
   const int64_t ktiles = (g.k + BK - 1) / BK;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(csmem);
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
@@ -126,16 +86,33 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 #pragma unroll
       for (int j = 0; j < 4; j++) accp[i][j] = accq[i][j] = 0ull;
 
+    TileLoader<true, 8, BM, BK, LDS, THREADS> la_mn, lb_mn;
+    KStager<float2, BM, BK, LDS, THREADS> la_k, lb_k;
+    if (A_MN) { if (vec_a) la_mn.init(A, g.lda, m0, g.m, tid); } else la_k.init(A, g.lda, m0, g.m, vec_a, tid);
+    if (B_MN) { if (vec_b) lb_mn.init(B, g.ldb, n0, g.n, tid); } else lb_k.init(B, g.ldb, n0, g.n, vec_b, tid);
     float2 ra[4], rb[4];
+    auto request = [&](int64_t kt_load) {
+      const int stage = (int)(kt_load % STAGES);
+      const int64_t k_left = g.k - kt_load * BK;
+      float2 *sa = csmem + stage * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
+      const uint32_t ua = smem_base + (uint32_t)(stage * STAGE_ELEMS * 8), ub = ua + (uint32_t)(OPERAND_ELEMS * 8);
+      if (A_MN) {
+        if (vec_a) { if (k_left < BK) la_mn.issue_tail(ua, (int)k_left); else la_mn.issue(ua); la_mn.advance(); }
+        else load_mn_unaligned(sa, A, g.lda, m0, kt_load * BK, g.m, g.k, tid);
+      } else { la_k.fetch(ra, k_left < BK ? (int)k_left : BK); la_k.advance(); }
+      if (B_MN) {
+        if (vec_b) { if (k_left < BK) lb_mn.issue_tail(ub, (int)k_left); else lb_mn.issue(ub); lb_mn.advance(); }
+        else load_mn_unaligned(sb, B, g.ldb, n0, kt_load * BK, g.n, g.k, tid);
+      } else { lb_k.fetch(rb, k_left < BK ? (int)k_left : BK); lb_k.advance(); }
+    };
+    auto deposit = [&](int64_t kt_load) {
+      float2 *sa = csmem + (kt_load % STAGES) * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
+      if (!A_MN) la_k.store(sa, ra);
+      if (!B_MN) lb_k.store(sb, rb);
+    };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-      if (s < ktiles) {
-        float2 *sa = csmem + s * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
-        if (A_MN) load_mn_async(sa, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, vec_a, tid);
-        else { fetch_k(ra, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, vec_a, tid); store_k(sa, ra, tid); }
-        if (B_MN) load_mn_async(sb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, vec_b, tid);
-        else { fetch_k(rb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, vec_b, tid); store_k(sb, rb, tid); }
-      }
+      if (s < ktiles) { request(s); deposit(s); }
       cp_async_commit();
     }
 
@@ -144,13 +121,7 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       __syncthreads();
       const int64_t nk = kt + STAGES - 1;
       const bool refill = nk < ktiles;
-      float2 *na = csmem + (nk % STAGES) * STAGE_ELEMS, *nb = na + OPERAND_ELEMS;
-      if (refill) {
-        if (A_MN) load_mn_async(na, A, g.lda, m0, nk * BK, g.m, g.k, vec_a, tid);
-        else fetch_k(ra, A, g.lda, m0, nk * BK, g.m, g.k, vec_a, tid);
-        if (B_MN) load_mn_async(nb, B, g.ldb, n0, nk * BK, g.n, g.k, vec_b, tid);
-        else fetch_k(rb, B, g.ldb, n0, nk * BK, g.n, g.k, vec_b, tid);
-      }
+      if (refill) request(nk);
       cp_async_commit();
 
       const float2 *sa = csmem + (kt % STAGES) * STAGE_ELEMS + tm * 2;
@@ -174,10 +145,7 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
           }
         }
       }
-      if (refill) {
-        if (!A_MN) store_k(na, ra, tid);
-        if (!B_MN) store_k(nb, rb, tid);
-      }
+      if (refill) deposit(nk);
     }
     cp_async_wait<0>();
     __syncthreads();

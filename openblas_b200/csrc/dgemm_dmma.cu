@@ -30,85 +30,64 @@
  */
 #include "gemm_common.cuh"
 #include "async_copy.cuh"
+#include <cstdlib>
 
 namespace b200 {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 4;
-constexpr int THREADS = 256;                 /* 8 warps: 2 (m) x 4 (n), warp tile 64 x 32 */
-constexpr int WM = 64, WN = 32;
-constexpr int LD_MN = BM + 4;                /* S[k][mn] row stride */
-constexpr int LD_K = BK + 4;                 /* S[mn][k] row stride */
-constexpr int OPERAND_DOUBLES = (BK * LD_MN > BM * LD_K) ? BK * LD_MN : BM * LD_K;  /* 2560 */
-constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);      /* 160 KB */
 
-/* Copy one (128 mn) x (16 k) operand tile global -> shared, zero-filling everything outside
- * the matrix.  MN_CONTIG: element (mn, k) lives at g[mn + k*ld], else at g[k + mn*ld].
- * vec16: the operand's base and ld allow 16-byte copies. */
-template <bool MN_CONTIG>
-__device__ __forceinline__ void load_tile(double *s, const double *__restrict__ g, int64_t ld, int64_t mn0,
-                                          int64_t k0, int64_t mn_end, int64_t k_end, bool vec16, int tid) {
-  if (MN_CONTIG) {
-    if (vec16) {
-#pragma unroll
-      for (int i = 0; i < (BM / 2) * BK / THREADS; i++) {   /* 4 */
-        int idx = tid + i * THREADS;
-        int k = idx / (BM / 2), mn = (idx % (BM / 2)) * 2;
-        int64_t gk = k0 + k, gmn = mn0 + mn;
-        int64_t left = (gk < k_end) ? (mn_end - gmn) : 0;
-        int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-        const double *src = bytes ? g + gmn + gk * ld : g;
-        cp_async16(s + k * LD_MN + mn, src, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < BM * BK / THREADS; i++) {         /* 8 */
-        int idx = tid + i * THREADS;
-        int k = idx / BM, mn = idx % BM;
-        int64_t gk = k0 + k, gmn = mn0 + mn;
-        int bytes = (gk < k_end && gmn < mn_end) ? 8 : 0;
-        const double *src = bytes ? g + gmn + gk * ld : g;
-        cp_async8(s + k * LD_MN + mn, src, bytes);
-      }
-    }
-  } else {
-    if (vec16) {
-#pragma unroll
-      for (int i = 0; i < BM * (BK / 2) / THREADS; i++) {   /* 4 */
-        int idx = tid + i * THREADS;
-        int k = (idx % (BK / 2)) * 2, mn = idx / (BK / 2);
-        int64_t gk = k0 + k, gmn = mn0 + mn;
-        int64_t left = (gmn < mn_end) ? (k_end - gk) : 0;
-        int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-        const double *src = bytes ? g + gk + gmn * ld : g;
-        cp_async16(s + mn * LD_K + k, src, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < BM * BK / THREADS; i++) {         /* 8 */
-        int idx = tid + i * THREADS;
-        int k = idx % BK, mn = idx / BK;
-        int64_t gk = k0 + k, gmn = mn0 + mn;
-        int bytes = (gk < k_end && gmn < mn_end) ? 8 : 0;
-        const double *src = bytes ? g + gk + gmn * ld : g;
-        cp_async8(s + mn * LD_K + k, src, bytes);
-      }
-    }
+/* Tile configuration.  DMMA.8x8x4 can be re-issued by the same warp only every ~32 cycles while
+ * the pipe needs 16 per instruction (measured: ncu shows the warp parked on the NOP that follows
+ * every DMMA), so two warps per scheduler can only just saturate the pipe and every LDS / barrier
+ * stall shows up as idle pipe time (80 % with 8 warps of 64x32).  Four warps per scheduler with
+ * 32x32 warp tiles (<= 128 registers) leave slack to hide them. */
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_, int MINB_>
+struct Cfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int LD_K = BK + 4;                     /* S[mn][k] row stride, = 4 mod 16 */
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int FM = WM / 8, FN = WN / 8;          /* 8x8 fragments per warp tile */
+  static constexpr int LDA_MN = BM + 4, LDB_MN = BN + 4;  /* S[k][mn] row strides, = 4 mod 16 */
+  static constexpr int A_DOUBLES = (BK * LDA_MN > BM * LD_K) ? BK * LDA_MN : BM * LD_K;
+  static constexpr int B_DOUBLES = (BK * LDB_MN > BN * LD_K) ? BK * LDB_MN : BN * LD_K;
+  static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+  static_assert(BM % 16 == 0 && BN % 16 == 0 && BK % 16 == 0, "strides must stay 4 mod 16");
+  static_assert(SMEM_BYTES <= 227 * 1024, "tile ring does not fit in shared memory");
+};
+
+/* Element-wise fallback loader for operands whose base or leading dimension is not 16-byte
+ * aligned (8-byte cp.async per element, bounds checked per element).  The aligned case uses
+ * TileLoader (async_copy.cuh).  MN_CONTIG: element (mn, k) lives at g[mn + k*ld], else at
+ * g[k + mn*ld]. */
+template <bool MN_CONTIG, int ROWS, int BK, int LD_MN, int THREADS>
+__device__ __noinline__ void load_tile_unaligned(double *s, const double *__restrict__ g, int64_t ld, int64_t mn0,
+                                                 int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
+  for (int i = 0; i < ROWS * BK / THREADS; i++) {
+    int idx = tid + i * THREADS;
+    int k = MN_CONTIG ? idx / ROWS : idx % BK, mn = MN_CONTIG ? idx % ROWS : idx / BK;
+    int64_t gk = k0 + k, gmn = mn0 + mn;
+    int bytes = (gk < k_end && gmn < mn_end) ? 8 : 0;
+    const double *src = bytes ? (MN_CONTIG ? g + gmn + gk * ld : g + gk + gmn * ld) : g;
+    cp_async8(MN_CONTIG ? s + k * LD_MN + mn : s + mn * (BK + 4) + k, src, bytes);
   }
 }
 
 /* A_MN: op(A) tile is stored mn-contiguous (A not transposed); B_MN: B transposed. */
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(THREADS, 1)
+template <class C_, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(C_::THREADS, C_::MINB)
 dgemm_dmma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
+  constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, LD_K = C_::LD_K, STAGES = C_::STAGES, THREADS = C_::THREADS;
+  constexpr int FM = C_::FM, FN = C_::FN;
+  constexpr int LDA_MN = C_::LDA_MN, LDB_MN = C_::LDB_MN;
+  constexpr int A_DOUBLES = C_::A_DOUBLES, STAGE_DOUBLES = C_::STAGE_DOUBLES;
   extern __shared__ __align__(16) double smem[];
   const double *__restrict__ A = (const double *)g.a;
   const double *__restrict__ B = (const double *)g.b;
   double *__restrict__ C = (double *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+  const int wm = (warp % C_::WARPS_M) * C_::WM, wn = (warp / C_::WARPS_M) * C_::WN;
   const int fi = lane >> 2, fk = lane & 3;          /* fragment index / k within a k4 step */
 
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
@@ -118,61 +97,76 @@ dgemm_dmma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const bool use_beta = beta != 0.0;
 
   /* per-lane fragment offsets inside an operand tile */
-  const int a_off = A_MN ? (fk * LD_MN + wm + fi) : ((wm + fi) * LD_K + fk);
-  const int b_off = B_MN ? (fk * LD_MN + wn + fi) : ((wn + fi) * LD_K + fk);
+  const int a_off = A_MN ? (fk * LDA_MN + wm + fi) : ((wm + fi) * LD_K + fk);
+  const int b_off = B_MN ? (fk * LDB_MN + wn + fi) : ((wn + fi) * LD_K + fk);
   constexpr int A_MT = A_MN ? 8 : 8 * LD_K;          /* step to the next 8-row m fragment */
   constexpr int B_NT = B_MN ? 8 : 8 * LD_K;
-  constexpr int A_K4 = A_MN ? 4 * LD_MN : 4;         /* step to the next k4 slice */
-  constexpr int B_K4 = B_MN ? 4 * LD_MN : 4;
+  constexpr int A_K4 = A_MN ? 4 * LDA_MN : 4;        /* step to the next k4 slice */
+  constexpr int B_K4 = B_MN ? 4 * LDB_MN : 4;
+
+  using LoadA = TileLoader<A_MN, 8, BM, BK, A_MN ? LDA_MN : LD_K, THREADS>;
+  using LoadB = TileLoader<B_MN, 8, BN, BK, B_MN ? LDB_MN : LD_K, THREADS>;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const int k_tail = (int)(g.k % BK);               /* != 0: the last k tile is partial */
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
     banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
 
-    double acc[8][4][2];
+    LoadA la; LoadB lb;
+    if (vec_a) la.init(A, g.lda, m0, g.m, tid);
+    if (vec_b) lb.init(B, g.ldb, n0, g.n, tid);
+    /* k tiles are requested strictly in order, so the loaders just advance */
+    int load_slot = 0;                               /* ring slot of the next k tile to request */
+    auto load_stage = [&](int64_t kt_load) {
+      const int stage = load_slot;
+      load_slot = (load_slot + 1 == STAGES) ? 0 : load_slot + 1;
+      const bool tail = k_tail != 0 && kt_load == ktiles - 1;
+      const uint32_t sa = smem_base + (uint32_t)(stage * STAGE_DOUBLES * 8), sb = sa + (uint32_t)(A_DOUBLES * 8);
+      if (vec_a) { if (tail) la.issue_tail(sa, k_tail); else la.issue(sa); la.advance(); }
+      else load_tile_unaligned<A_MN, BM, BK, LDA_MN, THREADS>(smem + stage * STAGE_DOUBLES, A, g.lda, m0, kt_load * BK, g.m, g.k, tid);
+      if (vec_b) { if (tail) lb.issue_tail(sb, k_tail); else lb.issue(sb); lb.advance(); }
+      else load_tile_unaligned<B_MN, BN, BK, LDB_MN, THREADS>(smem + stage * STAGE_DOUBLES + A_DOUBLES, B, g.ldb, n0, kt_load * BK, g.n, g.k, tid);
+    };
+
+    double acc[FM][FN][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < FM; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     /* prologue: STAGES-1 tiles in flight */
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-      if (s < ktiles) {
-        double *sa = smem + s * STAGE_DOUBLES, *sb = sa + OPERAND_DOUBLES;
-        load_tile<A_MN>(sa, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, vec_a, tid);
-        load_tile<B_MN>(sb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, vec_b, tid);
-      }
+      if (s < ktiles) load_stage(s);
       cp_async_commit();
     }
 
+    int slot = 0;                                    /* ring slot of the k tile being consumed */
     for (int64_t kt = 0; kt < ktiles; kt++) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       {
         /* refill the stage consumed in the previous iteration */
         int64_t nk = kt + STAGES - 1;
-        if (nk < ktiles) {
-          double *sa = smem + (nk % STAGES) * STAGE_DOUBLES, *sb = sa + OPERAND_DOUBLES;
-          load_tile<A_MN>(sa, A, g.lda, m0, nk * BK, g.m, g.k, vec_a, tid);
-          load_tile<B_MN>(sb, B, g.ldb, n0, nk * BK, g.n, g.k, vec_b, tid);
-        }
+        if (nk < ktiles) load_stage(nk);
         cp_async_commit();
       }
-      const double *sa = smem + (kt % STAGES) * STAGE_DOUBLES + a_off;
-      const double *sb = smem + (kt % STAGES) * STAGE_DOUBLES + OPERAND_DOUBLES + b_off;
+      const double *sa = smem + slot * STAGE_DOUBLES + a_off;
+      const double *sb = smem + slot * STAGE_DOUBLES + A_DOUBLES + b_off;
+      slot = (slot + 1 == STAGES) ? 0 : slot + 1;
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; k4++) {
-        double af[8], bf[4];
+        double af[FM], bf[FN];
 #pragma unroll
-        for (int i = 0; i < 8; i++) af[i] = sa[k4 * A_K4 + i * A_MT];
+        for (int i = 0; i < FM; i++) af[i] = sa[k4 * A_K4 + i * A_MT];
 #pragma unroll
-        for (int j = 0; j < 4; j++) bf[j] = sb[k4 * B_K4 + j * B_NT];
+        for (int j = 0; j < FN; j++) bf[j] = sb[k4 * B_K4 + j * B_NT];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < FM; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+          for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
       }
     }
     cp_async_wait<0>();
@@ -180,11 +174,11 @@ dgemm_dmma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 
     /* epilogue: lane owns C[m .. m+1][n], m = m0+wm+8i+2*fk, n = n0+wn+8j+fi */
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < FN; j++) {
       const int64_t n = n0 + wn + 8 * j + fi;
       if (n >= g.n) continue;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < FM; i++) {
         const int64_t m = m0 + wm + 8 * i + 2 * fk;
         if (m >= g.m) continue;
         double *p = C + m + n * g.ldc;
@@ -208,36 +202,57 @@ dgemm_dmma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <class C_, bool A_MN, bool B_MN>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
   static bool configured = false;   /* per instantiation; benign race: same value every time */
-  auto kern = dgemm_dmma_kernel<A_MN, B_MN>;
+  auto kern = dgemm_dmma_kernel<C_, A_MN, B_MN>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int64_t tiles = ((g.m + BM - 1) / BM) * ((g.n + BN - 1) / BN);
-  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
+  int64_t tiles = ((g.m + C_::BM - 1) / C_::BM) * ((g.n + C_::BN - 1) / C_::BN);
+  int64_t cap = (int64_t)sm_count() * C_::MINB;
+  int grid = (int)(tiles < cap ? tiles : cap);
+  kern<<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
   return cudaGetLastError();
 }
+
+template <class C_>
+cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
+  const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  const int vec_a = (((uintptr_t)g.a & 15) == 0) && (g.lda % 2 == 0);
+  const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 2 == 0);
+  const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
+  if (a_mn && b_mn) return launch_variant<C_, true, true>(g, stream, vec_a, vec_b, vec_c);
+  if (a_mn && !b_mn) return launch_variant<C_, true, false>(g, stream, vec_a, vec_b, vec_c);
+  if (!a_mn && b_mn) return launch_variant<C_, false, true>(g, stream, vec_a, vec_b, vec_c);
+  return launch_variant<C_, false, false>(g, stream, vec_a, vec_b, vec_c);
+}
+
+using CfgWide   = Cfg<128, 128, 64, 32, 16, 4, 1>;   /* 8 warps, 64x32 warp tiles, k step 16, 1 CTA/SM            */
+using CfgDual   = Cfg<128, 64, 32, 32, 16, 3, 2>;    /* 8 warps, 32x32 warp tiles, 2 CTAs/SM: 16 warps per SM     */
+using CfgBig    = Cfg<128, 128, 32, 32, 16, 4, 1>;   /* 16 warps, 32x32 warp tiles, 1 CTA/SM                      */
+using CfgWide32 = Cfg<128, 128, 64, 32, 32, 3, 1>;   /* as Wide with k step 32: half as many barriers per flop    */
+using CfgWide32b = Cfg<128, 128, 64, 32, 32, 2, 1>;  /* k step 32, double buffer                                  */
 
 }  // namespace
 
 cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   if (g.dtype != B200_D) return cudaErrorNotSupported;
   if (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 7) return cudaErrorNotSupported;
-  const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
-  const int vec_a = (((uintptr_t)g.a & 15) == 0) && (g.lda % 2 == 0);
-  const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 2 == 0);
-  const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
+  static int cfg = -1;
+  if (cfg < 0) { const char *e = getenv("B200_DGEMM_CFG"); cfg = e ? atoi(e) : 3; }
   cudaError_t e;
-  if (a_mn && b_mn) e = launch_variant<true, true>(g, stream, vec_a, vec_b, vec_c);
-  else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream, vec_a, vec_b, vec_c);
-  else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream, vec_a, vec_b, vec_c);
-  else e = launch_variant<false, false>(g, stream, vec_a, vec_b, vec_c);
-  if (e == cudaSuccess) count_launch("dgemm_dmma_128x128x16");
+  const char *name;
+  switch (cfg) {
+    case 1:  e = launch_cfg<CfgDual>(g, stream); name = "dgemm_dmma_128x64x16_w32x32_2cta"; break;
+    case 2:  e = launch_cfg<CfgBig>(g, stream);  name = "dgemm_dmma_128x128x16_w32x32"; break;
+    case 0:  e = launch_cfg<CfgWide>(g, stream); name = "dgemm_dmma_128x128x16_w64x32"; break;
+    case 4:  e = launch_cfg<CfgWide32b>(g, stream); name = "dgemm_dmma_128x128x32_w64x32_2stage"; break;
+    default: e = launch_cfg<CfgWide32>(g, stream); name = "dgemm_dmma_128x128x32_w64x32"; break;
+  }
+  if (e == cudaSuccess) count_launch(name);
   return e;
 }
 

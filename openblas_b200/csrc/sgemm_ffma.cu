@@ -19,6 +19,7 @@
  */
 #include "gemm_common.cuh"
 #include "async_copy.cuh"
+#include <cstdlib>
 
 namespace b200 {
 namespace {
@@ -45,62 +46,21 @@ __device__ __forceinline__ void ffma2(u64 &c, u64 a, u64 b) {
   asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
 }
 
-/* mn-contiguous operand: element (mn,k) at g[mn + k*ld] -> S[k][mn] by cp.async */
-__device__ __forceinline__ void load_mn_async(float *s, const float *__restrict__ g, int64_t ld, int64_t mn0,
-                                              int64_t k0, int64_t mn_end, int64_t k_end, bool vec, int tid) {
-  if (vec) {
-#pragma unroll
-    for (int i = 0; i < (BM / 4) * BK / THREADS; i++) {   /* 2 */
-      int idx = tid + i * THREADS;
-      int k = idx / (BM / 4), mn = (idx % (BM / 4)) * 4;
-      int64_t gk = k0 + k, gmn = mn0 + mn;
-      int64_t left = (gk < k_end) ? (mn_end - gmn) : 0;
-      int bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
-      const float *src = bytes ? g + gmn + gk * ld : g;
-      cp_async16(s + k * LDS + mn, src, bytes);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < BM * BK / THREADS; i++) {         /* 8 */
-      int idx = tid + i * THREADS;
-      int k = idx / BM, mn = idx % BM;
-      int64_t gk = k0 + k, gmn = mn0 + mn;
-      int bytes = (gk < k_end && gmn < mn_end) ? 4 : 0;
-      const float *src = bytes ? g + gmn + gk * ld : g;
-      cp_async4(s + k * LDS + mn, src, bytes);
-    }
+/* Element-wise fallback for an mn-contiguous operand that is not 16-byte aligned. */
+__device__ __noinline__ void load_mn_unaligned(float *s, const float *__restrict__ g, int64_t ld, int64_t mn0,
+                                               int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
+  for (int i = 0; i < BM * BK / THREADS; i++) {
+    int idx = tid + i * THREADS;
+    int k = idx / BM, mn = idx % BM;
+    int64_t gk = k0 + k, gmn = mn0 + mn;
+    int bytes = (gk < k_end && gmn < mn_end) ? 4 : 0;
+    const float *src = bytes ? g + gmn + gk * ld : g;
+    cp_async4(s + k * LDS + mn, src, bytes);
   }
 }
 
-/* k-contiguous operand: element (mn,k) at g[k + mn*ld].  Each thread owns two (mn, 4 k) quads. */
-__device__ __forceinline__ void fetch_k(float (&r)[8], const float *__restrict__ g, int64_t ld, int64_t mn0,
-                                        int64_t k0, int64_t mn_end, int64_t k_end, bool vec, int tid) {
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    int idx = tid + i * THREADS;
-    int kq = (idx % 4) * 4, mn = idx / 4;
-    int64_t gk = k0 + kq, gmn = mn0 + mn;
-    if (gmn < mn_end && gk + 3 < k_end && vec) {
-      float4 v = *reinterpret_cast<const float4 *>(g + gk + gmn * ld);
-      r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-        r[4 * i + e] = (gmn < mn_end && gk + e < k_end) ? g[gk + e + gmn * ld] : 0.f;
-    }
-  }
-}
-__device__ __forceinline__ void store_k(float *s, const float (&r)[8], int tid) {
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    int idx = tid + i * THREADS;
-    int kq = (idx % 4) * 4, mn = idx / 4;
-#pragma unroll
-    for (int e = 0; e < 4; e++) s[(kq + e) * LDS + mn] = r[4 * i + e];
-  }
-}
-
-template <bool A_MN, bool B_MN>
+/* PACKED: accumulate with FFMA2 (fma.rn.f32x2) on row pairs; otherwise with scalar FFMA. */
+template <bool A_MN, bool B_MN, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 2)
 sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   extern __shared__ __align__(16) float fsmem[];
@@ -117,6 +77,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const int64_t ktiles = (g.k + BK - 1) / BK;
   const float alpha = (float)g.alpha_re, beta = (float)g.beta_re;
   const bool use_beta = beta != 0.f;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fsmem);
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
@@ -125,21 +86,48 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 
     /* acc[p][j]: rows (2p, 2p+1) of the thread's 8 rows, column j of its 8 columns */
     u64 acc[4][8];
+    float accs[PACKED ? 1 : 8][PACKED ? 1 : 8];
 #pragma unroll
     for (int p = 0; p < 4; p++)
 #pragma unroll
       for (int j = 0; j < 8; j++) acc[p][j] = 0ull;
+    if (!PACKED) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) accs[PACKED ? 0 : i][PACKED ? 0 : j] = 0.f;
+    }
 
+    /* loaders with hoisted addresses; k tiles are requested strictly in order */
+    TileLoader<true, 4, BM, BK, LDS, THREADS> la_mn, lb_mn;
+    KStager<float, BM, BK, LDS, THREADS> la_k, lb_k;
+    if (A_MN) { if (vec_a) la_mn.init(A, g.lda, m0, g.m, tid); } else la_k.init(A, g.lda, m0, g.m, vec_a, tid);
+    if (B_MN) { if (vec_b) lb_mn.init(B, g.ldb, n0, g.n, tid); } else lb_k.init(B, g.ldb, n0, g.n, vec_b, tid);
     float ra[8], rb[8];
+    /* issue the asynchronous part of k tile `kt_load` (cp.async for mn-contiguous operands, global
+     * loads into registers for k-contiguous ones) */
+    auto request = [&](int64_t kt_load) {
+      const int stage = (int)(kt_load % STAGES);
+      const int64_t k_left = g.k - kt_load * BK;
+      float *sa = fsmem + stage * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
+      const uint32_t ua = smem_base + (uint32_t)(stage * STAGE_FLOATS * 4), ub = ua + (uint32_t)(OPERAND_FLOATS * 4);
+      if (A_MN) {
+        if (vec_a) { if (k_left < BK) la_mn.issue_tail(ua, (int)k_left); else la_mn.issue(ua); la_mn.advance(); }
+        else load_mn_unaligned(sa, A, g.lda, m0, kt_load * BK, g.m, g.k, tid);
+      } else { la_k.fetch(ra, k_left < BK ? (int)k_left : BK); la_k.advance(); }
+      if (B_MN) {
+        if (vec_b) { if (k_left < BK) lb_mn.issue_tail(ub, (int)k_left); else lb_mn.issue(ub); lb_mn.advance(); }
+        else load_mn_unaligned(sb, B, g.ldb, n0, kt_load * BK, g.n, g.k, tid);
+      } else { lb_k.fetch(rb, k_left < BK ? (int)k_left : BK); lb_k.advance(); }
+    };
+    auto deposit = [&](int64_t kt_load) {   /* register-staged operands: transpose into S[k][mn] */
+      float *sa = fsmem + (kt_load % STAGES) * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
+      if (!A_MN) la_k.store(sa, ra);
+      if (!B_MN) lb_k.store(sb, rb);
+    };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-      if (s < ktiles) {
-        float *sa = fsmem + s * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
-        if (A_MN) load_mn_async(sa, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, vec_a, tid);
-        else { fetch_k(ra, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, vec_a, tid); store_k(sa, ra, tid); }
-        if (B_MN) load_mn_async(sb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, vec_b, tid);
-        else { fetch_k(rb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, vec_b, tid); store_k(sb, rb, tid); }
-      }
+      if (s < ktiles) { request(s); deposit(s); }
       cp_async_commit();
     }
 
@@ -148,13 +136,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       __syncthreads();
       const int64_t nk = kt + STAGES - 1;
       const bool refill = nk < ktiles;
-      float *na = fsmem + (nk % STAGES) * STAGE_FLOATS, *nb = na + OPERAND_FLOATS;
-      if (refill) {
-        if (A_MN) load_mn_async(na, A, g.lda, m0, nk * BK, g.m, g.k, vec_a, tid);
-        else fetch_k(ra, A, g.lda, m0, nk * BK, g.m, g.k, vec_a, tid);
-        if (B_MN) load_mn_async(nb, B, g.ldb, n0, nk * BK, g.n, g.k, vec_b, tid);
-        else fetch_k(rb, B, g.ldb, n0, nk * BK, g.n, g.k, vec_b, tid);
-      }
+      if (refill) request(nk);
       cp_async_commit();
 
       const float *sa = fsmem + (kt % STAGES) * STAGE_FLOATS + tm * 4;
@@ -162,23 +144,31 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 #pragma unroll
       for (int k = 0; k < BK; k++) {
         /* rows tm*4..+3 and 64+tm*4..+3 as two 64-bit pairs each; columns likewise as floats */
-        ulonglong2 a_lo = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS);
-        ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS + 64);
         float4 b_lo = *reinterpret_cast<const float4 *>(sb + k * LDS);
         float4 b_hi = *reinterpret_cast<const float4 *>(sb + k * LDS + 64);
-        u64 ap[4] = {a_lo.x, a_lo.y, a_hi.x, a_hi.y};
         float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+        if (PACKED) {
+          ulonglong2 a_lo = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS);
+          ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS + 64);
+          u64 ap[4] = {a_lo.x, a_lo.y, a_hi.x, a_hi.y};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          u64 bb = pack2(bv[j], bv[j]);
+          for (int j = 0; j < 8; j++) {
+            u64 bb = pack2(bv[j], bv[j]);
 #pragma unroll
-          for (int p = 0; p < 4; p++) ffma2(acc[p][j], ap[p], bb);
+            for (int p = 0; p < 4; p++) ffma2(acc[p][j], ap[p], bb);
+          }
+        } else {
+          float4 a_lo = *reinterpret_cast<const float4 *>(sa + k * LDS);
+          float4 a_hi = *reinterpret_cast<const float4 *>(sa + k * LDS + 64);
+          float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              accs[PACKED ? 0 : i][PACKED ? 0 : j] = fmaf(av[i], bv[j], accs[PACKED ? 0 : i][PACKED ? 0 : j]);
         }
       }
-      if (refill) {
-        if (!A_MN) store_k(na, ra, tid);
-        if (!B_MN) store_k(nb, rb, tid);
-      }
+      if (refill) deposit(nk);
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -193,8 +183,13 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
         const int64_t m = m0 + h * 64 + tm * 4;
         if (m >= g.m) continue;
         float v[4];
-        unpack2(acc[2 * h][j], v[0], v[1]);
-        unpack2(acc[2 * h + 1][j], v[2], v[3]);
+        if (PACKED) {
+          unpack2(acc[2 * h][j], v[0], v[1]);
+          unpack2(acc[2 * h + 1][j], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) v[e] = accs[PACKED ? 0 : 4 * h + e][PACKED ? 0 : j];
+        }
         float *p = C + m + n * g.ldc;
         if (vec_c && m + 3 < g.m) {
           float4 o = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
@@ -218,10 +213,10 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PACKED>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
   static bool configured = false;
-  auto kern = sgemm_ffma_kernel<A_MN, B_MN>;
+  auto kern = sgemm_ffma_kernel<A_MN, B_MN, PACKED>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -243,12 +238,21 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   const int vec_a = (((uintptr_t)g.a & 15) == 0) && (g.lda % 4 == 0);
   const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 4 == 0);
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
+  static int packed = -1;
+  if (packed < 0) { const char *ev = getenv("B200_SGEMM_PACKED"); packed = ev ? atoi(ev) : 1; }
   cudaError_t e;
-  if (a_mn && b_mn) e = launch_variant<true, true>(g, stream, vec_a, vec_b, vec_c);
-  else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream, vec_a, vec_b, vec_c);
-  else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream, vec_a, vec_b, vec_c);
-  else e = launch_variant<false, false>(g, stream, vec_a, vec_b, vec_c);
-  if (e == cudaSuccess) count_launch("sgemm_ffma2_128x128x16");
+  if (packed) {
+    if (a_mn && b_mn) e = launch_variant<true, true, true>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_variant<true, false, true>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_variant<false, true, true>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_variant<false, false, true>(g, stream, vec_a, vec_b, vec_c);
+  } else {
+    if (a_mn && b_mn) e = launch_variant<true, true, false>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_variant<true, false, false>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_variant<false, true, false>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_variant<false, false, false>(g, stream, vec_a, vec_b, vec_c);
+  }
+  if (e == cudaSuccess) count_launch(packed ? "sgemm_ffma2_128x128x16" : "sgemm_ffma_128x128x16");
   return e;
 }
 

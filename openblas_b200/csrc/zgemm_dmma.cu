@@ -40,22 +40,6 @@ __device__ __forceinline__ double xor_sign(double x, int mask) {
   return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
 }
 
-/* (ROWS mn) x (8 k) complex tile, one 16-byte cp.async per element, zero fill outside. */
-template <bool MN_CONTIG, int ROWS, int LD_MN>
-__device__ __forceinline__ void load_tile(double2 *s, const double2 *__restrict__ g, int64_t ld, int64_t mn0,
-                                          int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
-#pragma unroll
-  for (int i = 0; i < ROWS * BK / THREADS; i++) {
-    int idx = tid + i * THREADS;
-    int k, mn;
-    if (MN_CONTIG) { k = idx / ROWS; mn = idx % ROWS; } else { k = idx % BK; mn = idx / BK; }
-    int64_t gk = k0 + k, gmn = mn0 + mn;
-    int bytes = (gk < k_end && gmn < mn_end) ? 16 : 0;
-    const double2 *src = bytes ? (MN_CONTIG ? g + gmn + gk * ld : g + gk + gmn * ld) : g;
-    cp_async16(MN_CONTIG ? s + k * LD_MN + mn : s + mn * LD_K + k, src, bytes);
-  }
-}
-
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 zgemm_dmma_kernel(DeviceGemm g) {
@@ -82,10 +66,28 @@ zgemm_dmma_kernel(DeviceGemm g) {
   constexpr int A_K4 = A_MN ? 4 * LDA_MN : 4;
   constexpr int B_K4 = B_MN ? 4 * LDB_MN : 4;
 
+  /* one complex = one 16-byte chunk; all address arithmetic hoisted out of the k loop */
+  using LoadA = TileLoader<A_MN, 16, BM, BK, A_MN ? LDA_MN : LD_K, THREADS>;
+  using LoadB = TileLoader<B_MN, 16, BN, BK, B_MN ? LDB_MN : LD_K, THREADS>;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(zsmem);
+  const int k_tail = (int)(g.k % BK);
+
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
     banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
+
+    LoadA la; LoadB lb;
+    la.init(A, g.lda, m0, g.m, tid);
+    lb.init(B, g.ldb, n0, g.n, tid);
+    int load_slot = 0;
+    auto load_stage = [&](int64_t kt_load) {
+      const uint32_t sa = smem_base + (uint32_t)(load_slot * STAGE_ELEMS * 16), sb = sa + (uint32_t)(A_ELEMS * 16);
+      load_slot = (load_slot + 1 == STAGES) ? 0 : load_slot + 1;
+      if (k_tail != 0 && kt_load == ktiles - 1) { la.issue_tail(sa, k_tail); lb.issue_tail(sb, k_tail); }
+      else { la.issue(sa); lb.issue(sb); }
+      la.advance(); lb.advance();
+    };
 
     double re[4][4][2], im[4][4][2];
 #pragma unroll
@@ -95,11 +97,7 @@ zgemm_dmma_kernel(DeviceGemm g) {
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-      if (s < ktiles) {
-        double2 *sa = zsmem + s * STAGE_ELEMS, *sb = sa + A_ELEMS;
-        load_tile<A_MN, BM, LDA_MN>(sa, A, g.lda, m0, (int64_t)s * BK, g.m, g.k, tid);
-        load_tile<B_MN, BN, LDB_MN>(sb, B, g.ldb, n0, (int64_t)s * BK, g.n, g.k, tid);
-      }
+      if (s < ktiles) load_stage(s);
       cp_async_commit();
     }
 
@@ -108,15 +106,12 @@ zgemm_dmma_kernel(DeviceGemm g) {
       __syncthreads();
       {
         int64_t nk = kt + STAGES - 1;
-        if (nk < ktiles) {
-          double2 *sa = zsmem + (nk % STAGES) * STAGE_ELEMS, *sb = sa + A_ELEMS;
-          load_tile<A_MN, BM, LDA_MN>(sa, A, g.lda, m0, nk * BK, g.m, g.k, tid);
-          load_tile<B_MN, BN, LDB_MN>(sb, B, g.ldb, n0, nk * BK, g.n, g.k, tid);
-        }
+        if (nk < ktiles) load_stage(nk);
         cp_async_commit();
       }
-      const double2 *sa = zsmem + (kt % STAGES) * STAGE_ELEMS + a_off;
-      const double2 *sb = zsmem + (kt % STAGES) * STAGE_ELEMS + A_ELEMS + b_off;
+      const int slot = (int)(kt % STAGES);   /* STAGES is a power of two */
+      const double2 *sa = zsmem + slot * STAGE_ELEMS + a_off;
+      const double2 *sb = zsmem + slot * STAGE_ELEMS + A_ELEMS + b_off;
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; k4++) {
         double ar[4], ai[4], nai[4], br[4], bi[4];
