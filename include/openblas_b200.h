@@ -165,8 +165,8 @@ enum b200_kernel {
 };
 
 /* Column-major C <- alpha*op(A)*op(B) + beta*C on DEVICE pointers, enqueued on `stream`
- * (a cudaStream_t passed as void*, NULL = the calling thread's library stream) without
- * synchronising.  alpha/beta are HOST pointers to one FLOAT (s,d,sb) or two (c,z).
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream, as everywhere in CUDA)
+ * without synchronising.  alpha/beta are HOST pointers to one FLOAT (s,d,sb) or two (c,z).
  * Arguments are assumed valid (the BLAS entry points validate).  Returns 0 or a
  * cudaError_t value. */
 int b200_gemm_async(int dtype, int transa, int transb, int64_t m, int64_t n, int64_t k,

@@ -403,14 +403,9 @@ B200_EXPORT int b200_gemm_async(int dtype, int transa, int transb, int64_t m, in
   g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a = A; g.b = B; g.c = C;
   read_scalars(&p, g);
   t_error[0] = 0;
-  if (stream) { CK(dispatch(g, (cudaStream_t)stream)); return 0; }
-  ContextLease lease;
-  err = acquire(&lease.c);
-  if (err) return err;
-  CK(dispatch(g, lease.c->stream));
-  /* the library stream is private: without a caller stream the only safe point to hand the
-   * context back is after completion */
-  CK(cudaStreamSynchronize(lease.c->stream));
+  /* CUDA convention: a NULL stream is the legacy default stream.  Nothing is synchronised here;
+   * ordering against the caller's other work is the caller's stream semantics. */
+  CK(dispatch(g, (cudaStream_t)stream));
   return 0;
 }
 

@@ -20,6 +20,7 @@ Matrices are column-major.  A local matrix is held as a 2-D torch tensor of shap
 
 torch.distributed is plumbing only (process groups, NCCL broadcast); the arithmetic is ours.
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -30,6 +31,11 @@ GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4), 16: (4, 4)}
 
 
 def grid_shape(world):
+    forced = os.environ.get("B200_SUMMA_GRID")      # e.g. "2x1": testing / odd topologies
+    if forced:
+        P, Q = (int(x) for x in forced.lower().split("x"))
+        assert P * Q == world, f"B200_SUMMA_GRID={forced} does not match world size {world}"
+        return P, Q
     if world in GRID:
         return GRID[world]
     p = int(world ** 0.5)

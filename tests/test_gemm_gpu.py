@@ -272,3 +272,28 @@ def test_concurrent_callers_get_identical_results(ob, oracle):
     for o in outs[1:]:
         assert np.array_equal(o.view(np.uint8), outs[0].view(np.uint8))
     check(oracle, cpu.D, 0, 0, m, n, k, 1.0, a, lda, b, ldb, 0.1, c0, ldc, outs[0], "threads")
+
+
+def test_summa_schedule_on_one_gpu(ob, oracle):
+    """The SUMMA panel loop (openblas_b200/summa.py: double-buffered panel copies on a side stream,
+    event hand-offs, per-panel DGEMM with beta applied only at the first panel) on a 1x1 grid must
+    equal one DGEMM of the whole problem."""
+    import torch
+    from openblas_b200 import summa
+    dev = torch.device("cuda", 0)
+    m, n, k, nb = 700, 520, 900, 128
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    A = torch.rand((k, m), generator=g, device=dev, dtype=torch.float64) - 0.5
+    B = torch.rand((n, k), generator=g, device=dev, dtype=torch.float64) - 0.5
+    C0 = torch.rand((n, m), generator=g, device=dev, dtype=torch.float64) - 0.5
+    grid = summa.Grid(1, 1, 0, 0, 0, None, None, [0], [0])
+    gemm = lambda mm, nn, kk, al, a, lda, b, ldb, be, c, ldc, st: ob.cblas.gemm_device(cpu.D, 0, 0, mm, nn, kk, al, a, lda, b, ldb, be, c, ldc, st)
+    sm = summa.Summa(grid, m, n, k, nb, torch.float64, dev, gemm)
+    got = C0.clone()
+    for _ in range(2):          # second sweep reuses the buffers / events
+        got.copy_(C0)
+        sm.run(0.7, A, B, 1.3, got)
+    torch.cuda.synchronize()
+    a, b, c0 = A.cpu().numpy(), B.cpu().numpy(), C0.cpu().numpy()
+    check(oracle, cpu.D, 0, 0, m, n, k, 0.7, a, m, b, k, 1.3, c0, m, got.cpu().numpy(), "summa-1gpu")
+    assert sm.launches == 2 * ((k + nb - 1) // nb)
