@@ -91,8 +91,10 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
     if (A_MN) { if (vec_a) la_mn.init(A, g.lda, m0, g.m, tid); } else la_k.init(A, g.lda, m0, g.m, vec_a, tid);
     if (B_MN) { if (vec_b) lb_mn.init(B, g.ldb, n0, g.n, tid); } else lb_k.init(B, g.ldb, n0, g.n, vec_b, tid);
     float2 ra[4], rb[4];
+    int req_slot = 0, dep_slot = 0, use_slot = 0;   /* ring positions: next request / deposit / consume */
     auto request = [&](int64_t kt_load) {
-      const int stage = (int)(kt_load % STAGES);
+      const int stage = req_slot;
+      req_slot = (req_slot + 1 == STAGES) ? 0 : req_slot + 1;
       const int64_t k_left = g.k - kt_load * BK;
       float2 *sa = csmem + stage * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
       const uint32_t ua = smem_base + (uint32_t)(stage * STAGE_ELEMS * 8), ub = ua + (uint32_t)(OPERAND_ELEMS * 8);
@@ -106,9 +108,10 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       } else { lb_k.fetch(rb, k_left < BK ? (int)k_left : BK); lb_k.advance(); }
     };
     auto deposit = [&](int64_t kt_load) {
-      float2 *sa = csmem + (kt_load % STAGES) * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
+      float2 *sa = csmem + dep_slot * STAGE_ELEMS, *sb = sa + OPERAND_ELEMS;
       if (!A_MN) la_k.store(sa, ra);
       if (!B_MN) lb_k.store(sb, rb);
+      dep_slot = (dep_slot + 1 == STAGES) ? 0 : dep_slot + 1;
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -124,8 +127,9 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       if (refill) request(nk);
       cp_async_commit();
 
-      const float2 *sa = csmem + (kt % STAGES) * STAGE_ELEMS + tm * 2;
-      const float2 *sb = csmem + (kt % STAGES) * STAGE_ELEMS + OPERAND_ELEMS + tn * 2;
+      const float2 *sa = csmem + use_slot * STAGE_ELEMS + tm * 2;
+      const float2 *sb = csmem + use_slot * STAGE_ELEMS + OPERAND_ELEMS + tn * 2;
+      use_slot = (use_slot + 1 == STAGES) ? 0 : use_slot + 1;
 #pragma unroll
       for (int k = 0; k < BK; k++) {
         ulonglong2 a01 = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS);

@@ -230,6 +230,206 @@ cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
   return launch_variant<C_, false, false>(g, stream, vec_a, vec_b, vec_c);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Bulk-copy variant for interior problems (m, n multiples of the tile, k a multiple of the k step,
+ * 16-byte aligned operands): the cp.async ring above costs every thread 8 LDGSTS plus their
+ * address registers per k tile and a CTA-wide barrier per k tile (ncu: stall_barrier 3 %,
+ * long_scoreboard 4 % on the address registers, short_scoreboard 6 %).  Here ONE extra warp is the
+ * producer: each of its lanes copies whole tile rows with the TMA engine's 1-D bulk copy
+ * (cp.async.bulk, SASS UBLKCP) into the same padded, conflict-free shared layout and completion
+ * is tracked by mbarriers (full[stage] with expect_tx, empty[stage] with one arrival per consumer
+ * warp), so the 8 DMMA warps never execute a load instruction for global memory, never hit a
+ * CTA-wide barrier in the main loop, and the producer runs ahead across C tiles (the next tile's
+ * first stages are in flight during the epilogue). */
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class C_, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(C_::THREADS + 32, 1)
+dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
+  constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, LD_K = C_::LD_K, STAGES = C_::STAGES;
+  constexpr int FM = C_::FM, FN = C_::FN;
+  constexpr int LDA_MN = C_::LDA_MN, LDB_MN = C_::LDB_MN;
+  constexpr int A_DOUBLES = C_::A_DOUBLES, STAGE_DOUBLES = C_::STAGE_DOUBLES;
+  constexpr uint32_t STAGE_TX = (uint32_t)(BM + BN) * BK * 8;          /* payload bytes per stage */
+  extern __shared__ __align__(16) double smem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t bars = smem_base + (uint32_t)(STAGES * STAGE_DOUBLES * 8);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+
+  const double *__restrict__ A = (const double *)g.a;
+  const double *__restrict__ B = (const double *)g.b;
+  double *__restrict__ C = (double *)g.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles_m = g.m / BM, tiles_n = g.n / BN, tiles = tiles_m * tiles_n;
+  const int64_t ktiles = g.k / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), C_::THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == C_::THREADS / 32) {
+    /* =============================================================== producer warp */
+    int slot = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      int64_t bm, bn;
+      banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+      const int64_t m0 = bm * BM, n0 = bn * BN;
+      for (int64_t kt = 0; kt < ktiles; kt++) {
+        const int64_t k0 = kt * BK;
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        if (probe_noload && kt >= STAGES) {           /* measurement probe: pure compute, stale tiles */
+          if (lane == 0) mbar_arrive(full_bar(slot));
+          __syncwarp();
+          if (++slot == STAGES) { slot = 0; phase ^= 1; }
+          continue;
+        }
+        if (lane == 0) mbar_expect_tx(full_bar(slot), STAGE_TX);
+        __syncwarp();
+        const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_DOUBLES * 8), sb = sa + (uint32_t)(A_DOUBLES * 8);
+        if (A_MN) {       /* BK rows (k) of BM contiguous doubles */
+          for (int r = lane; r < BK; r += 32)
+            bulk_copy(sa + (uint32_t)(r * LDA_MN * 8), A + m0 + (k0 + r) * g.lda, BM * 8, full_bar(slot));
+        } else {          /* BM rows (m) of BK contiguous doubles */
+          for (int r = lane; r < BM; r += 32)
+            bulk_copy(sa + (uint32_t)(r * LD_K * 8), A + k0 + (m0 + r) * g.lda, BK * 8, full_bar(slot));
+        }
+        if (B_MN) {
+          for (int r = lane; r < BK; r += 32)
+            bulk_copy(sb + (uint32_t)(r * LDB_MN * 8), B + n0 + (k0 + r) * g.ldb, BN * 8, full_bar(slot));
+        } else {
+          for (int r = lane; r < BN; r += 32)
+            bulk_copy(sb + (uint32_t)(r * LD_K * 8), B + k0 + (n0 + r) * g.ldb, BK * 8, full_bar(slot));
+        }
+        if (++slot == STAGES) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  /* ================================================================= consumer warps */
+  const int wm = (warp % C_::WARPS_M) * C_::WM, wn = (warp / C_::WARPS_M) * C_::WN;
+  const int fi = lane >> 2, fk = lane & 3;
+  const double alpha = g.alpha_re, beta = g.beta_re;
+  const bool use_beta = beta != 0.0;
+  const int a_off = A_MN ? (fk * LDA_MN + wm + fi) : ((wm + fi) * LD_K + fk);
+  const int b_off = B_MN ? (fk * LDB_MN + wn + fi) : ((wn + fi) * LD_K + fk);
+  constexpr int A_MT = A_MN ? 8 : 8 * LD_K;
+  constexpr int B_NT = B_MN ? 8 : 8 * LD_K;
+  constexpr int A_K4 = A_MN ? 4 * LDA_MN : 4;
+  constexpr int B_K4 = B_MN ? 4 * LDB_MN : 4;
+
+  int slot = 0; uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    int64_t bm, bn;
+    banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+    const int64_t m0 = bm * BM, n0 = bn * BN;
+
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+      for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int64_t kt = 0; kt < ktiles; kt++) {
+      mbar_wait(full_bar(slot), phase);
+      const double *sa = smem + slot * STAGE_DOUBLES + a_off;
+      const double *sb = smem + slot * STAGE_DOUBLES + A_DOUBLES + b_off;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; k4++) {
+        double af[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; i++) af[i] = sa[k4 * A_K4 + i * A_MT];
+#pragma unroll
+        for (int j = 0; j < FN; j++) bf[j] = sb[k4 * B_K4 + j * B_NT];
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+          for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(slot));     /* this warp is done reading the stage */
+      if (++slot == STAGES) { slot = 0; phase ^= 1; }
+    }
+
+    /* epilogue (interior tile: no bounds checks; 16-byte stores need ldc even, C 16-byte aligned) */
+#pragma unroll
+    for (int j = 0; j < FN; j++) {
+      const int64_t n = n0 + wn + 8 * j + fi;
+#pragma unroll
+      for (int i = 0; i < FM; i++) {
+        const int64_t m = m0 + wm + 8 * i + 2 * fk;
+        double *p = C + m + n * g.ldc;
+        double r0 = alpha * acc[i][j][0], r1 = alpha * acc[i][j][1];
+        if (use_beta) {
+          double2 old = *reinterpret_cast<const double2 *>(p);
+          r0 = fma(beta, old.x, r0); r1 = fma(beta, old.y, r1);
+        }
+        *reinterpret_cast<double2 *>(p) = make_double2(r0, r1);
+      }
+    }
+  }
+}
+
+template <class C_, bool A_MN, bool B_MN>
+cudaError_t launch_bulk_variant(const DeviceGemm &g, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = dgemm_dmma_bulk_kernel<C_, A_MN, B_MN>;
+  constexpr size_t smem_bytes = C_::SMEM_BYTES + 64;
+  static_assert(smem_bytes <= 227 * 1024, "bulk ring does not fit");
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t tiles = (g.m / C_::BM) * (g.n / C_::BN);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  static int probe = -1;   /* B200_DGEMM_PROBE_NOLOAD=1: timing probe only, results are garbage */
+  if (probe < 0) { const char *e = getenv("B200_DGEMM_PROBE_NOLOAD"); probe = e ? atoi(e) : 0; }
+  kern<<<grid, C_::THREADS + 32, smem_bytes, stream>>>(g, probe);
+  return cudaGetLastError();
+}
+
+template <class C_>
+bool bulk_eligible(const DeviceGemm &g) {
+  return g.m % C_::BM == 0 && g.n % C_::BN == 0 && g.k % C_::BK == 0 && g.lda % 2 == 0 && g.ldb % 2 == 0 &&
+         g.ldc % 2 == 0 && ((((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 15) == 0);
+}
+
+template <class C_>
+cudaError_t launch_bulk(const DeviceGemm &g, cudaStream_t stream) {
+  const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  if (a_mn && b_mn) return launch_bulk_variant<C_, true, true>(g, stream);
+  if (a_mn && !b_mn) return launch_bulk_variant<C_, true, false>(g, stream);
+  if (!a_mn && b_mn) return launch_bulk_variant<C_, false, true>(g, stream);
+  return launch_bulk_variant<C_, false, false>(g, stream);
+}
+
 using CfgWide   = Cfg<128, 128, 64, 32, 16, 4, 1>;   /* 8 warps, 64x32 warp tiles, k step 16, 1 CTA/SM            */
 using CfgDual   = Cfg<128, 64, 32, 32, 16, 3, 2>;    /* 8 warps, 32x32 warp tiles, 2 CTAs/SM: 16 warps per SM     */
 using CfgBig    = Cfg<128, 128, 32, 32, 16, 4, 1>;   /* 16 warps, 32x32 warp tiles, 1 CTA/SM                      */
@@ -242,9 +442,14 @@ cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   if (g.dtype != B200_D) return cudaErrorNotSupported;
   if (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 7) return cudaErrorNotSupported;
   static int cfg = -1;
-  if (cfg < 0) { const char *e = getenv("B200_DGEMM_CFG"); cfg = e ? atoi(e) : 3; }
+  if (cfg < 0) { const char *e = getenv("B200_DGEMM_CFG"); cfg = e ? atoi(e) : 5; }
   cudaError_t e;
   const char *name;
+  if (cfg >= 5 && bulk_eligible<CfgWide32>(g)) {
+    e = launch_bulk<CfgWide32>(g, stream);
+    if (e == cudaSuccess) count_launch("dgemm_dmma_bulk_128x128x32_w64x32");
+    return e;
+  }
   switch (cfg) {
     case 1:  e = launch_cfg<CfgDual>(g, stream); name = "dgemm_dmma_128x64x16_w32x32_2cta"; break;
     case 2:  e = launch_cfg<CfgBig>(g, stream);  name = "dgemm_dmma_128x128x16_w32x32"; break;

@@ -106,8 +106,10 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
     float ra[8], rb[8];
     /* issue the asynchronous part of k tile `kt_load` (cp.async for mn-contiguous operands, global
      * loads into registers for k-contiguous ones) */
+    int req_slot = 0, dep_slot = 0, use_slot = 0;   /* ring positions: next request / deposit / consume */
     auto request = [&](int64_t kt_load) {
-      const int stage = (int)(kt_load % STAGES);
+      const int stage = req_slot;
+      req_slot = (req_slot + 1 == STAGES) ? 0 : req_slot + 1;
       const int64_t k_left = g.k - kt_load * BK;
       float *sa = fsmem + stage * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
       const uint32_t ua = smem_base + (uint32_t)(stage * STAGE_FLOATS * 4), ub = ua + (uint32_t)(OPERAND_FLOATS * 4);
@@ -121,9 +123,10 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       } else { lb_k.fetch(rb, k_left < BK ? (int)k_left : BK); lb_k.advance(); }
     };
     auto deposit = [&](int64_t kt_load) {   /* register-staged operands: transpose into S[k][mn] */
-      float *sa = fsmem + (kt_load % STAGES) * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
+      float *sa = fsmem + dep_slot * STAGE_FLOATS, *sb = sa + OPERAND_FLOATS;
       if (!A_MN) la_k.store(sa, ra);
       if (!B_MN) lb_k.store(sb, rb);
+      dep_slot = (dep_slot + 1 == STAGES) ? 0 : dep_slot + 1;
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -139,8 +142,9 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       if (refill) request(nk);
       cp_async_commit();
 
-      const float *sa = fsmem + (kt % STAGES) * STAGE_FLOATS + tm * 4;
-      const float *sb = fsmem + (kt % STAGES) * STAGE_FLOATS + OPERAND_FLOATS + tn * 4;
+      const float *sa = fsmem + use_slot * STAGE_FLOATS + tm * 4;
+      const float *sb = fsmem + use_slot * STAGE_FLOATS + OPERAND_FLOATS + tn * 4;
+      use_slot = (use_slot + 1 == STAGES) ? 0 : use_slot + 1;
 #pragma unroll
       for (int k = 0; k < BK; k++) {
         /* rows tm*4..+3 and 64+tm*4..+3 as two 64-bit pairs each; columns likewise as floats */

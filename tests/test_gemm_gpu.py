@@ -297,3 +297,27 @@ def test_summa_schedule_on_one_gpu(ob, oracle):
     a, b, c0 = A.cpu().numpy(), B.cpu().numpy(), C0.cpu().numpy()
     check(oracle, cpu.D, 0, 0, m, n, k, 0.7, a, m, b, k, 1.3, c0, m, got.cpu().numpy(), "summa-1gpu")
     assert sm.launches == 2 * ((k + nb - 1) // nb)
+
+
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.S, cpu.Z, cpu.CX, cpu.SB])
+def test_tile_aligned_shapes_take_the_roofline_kernels(ob, oracle, dtype):
+    """Shapes that are multiples of every kernel's tile with 16-byte friendly leading dimensions:
+    the paths the benchmarks run (DGEMM: the bulk-copy/mbarrier variant), all op combinations,
+    beta != 0, several C tiles per CTA and several ring wraps."""
+    import torch
+    rng = np.random.default_rng(5000 + dtype)
+    shapes = [(256, 512, 256), (384, 768, 416)]     # kept small: the CPU oracle is O(mnk) scalar code
+    for (m, n, k) in shapes:
+        for ta in range(ntrans(dtype)):
+            for tb in range(ntrans(dtype)):
+                a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(8, 16, 24))
+                alpha, beta = alpha_beta(dtype)[0][2], alpha_beta(dtype)[1][2]
+                view = {np.uint16: np.int16}.get(a.dtype.type, a.dtype.type)
+                da, db = torch.from_numpy(a.view(view)).cuda(), torch.from_numpy(b.view(view)).cuda()
+                dc = torch.from_numpy(c0.copy()).cuda()
+                ob.cblas.gemm_any(dtype, ta, tb, m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc)
+                kern = ob.cblas.last_kernel()
+                assert "generic" not in kern, kern
+                check(oracle, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, dc.cpu().numpy(), kern)
+    if dtype == cpu.D:
+        assert "bulk" in kern, kern
