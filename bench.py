@@ -33,6 +33,9 @@ FLOP_FACTOR = {"s": 2.0, "d": 2.0, "c": 8.0, "z": 8.0, "sb": 2.0}   # real flops
 # that file: measured on this pool's B200 with tools/peaks.cu (profiles/r01_peaks_microbench.json):
 # DMMA.8x8x4 issue rate 36.8 TFLOP/s, FFMA 71.1 TFLOP/s (cuBLAS: dgemm 36.0, sgemm-pedantic 66.8).
 PEAK_FALLBACK = {"d": 36.8, "z": 36.8, "s": 71.1, "c": 71.1, "sb": 1590.0}
+# DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from one
+# `ncu --set full` capture of the same shape: profiles/r01_dgemm16384_ncu_full_summary.txt
+NCU_TRAFFIC_BYTES = {("d", 16384, 16384, 16384): 60.937608e9 + 2.152380e9}
 
 
 def measured_peak(dtype):
@@ -91,6 +94,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(dtype, m, n, k, parallelism):
+    """The `config` object both arms print (same workload naming for the driver's ratio)."""
+    return {"workload": f"{dtype}gemm NN column-major {m}x{n}x{k} alpha=1 beta=0 (BASELINE configs[1] at N=1; configs[3] shape at N=8)",
+            "parallelism": parallelism, "l2_policy": "inputs larger than L2 (A,B >= 2 GiB each vs 126 MB L2)",
+            "inputs": "uniform(-0.5,0.5), fixed seed, resident in HBM"}
+
+
 def weak_shape(world):
     return {1: (16384, 16384, 16384), 2: (16384, 32768, 16384), 4: (32768, 32768, 16384), 8: (32768, 32768, 32768)}.get(
         world, (16384, 16384 * world, 16384))
@@ -138,12 +148,16 @@ def run_reference(args):
     flops = 2.0 * n * n * n * args.steps      # BASELINE metric is 2mnk/t for every precision
     val = flops / dt / 1e12
     sample = f"{dtype.upper()}GEMM {n}^3 NN column-major alpha=1 beta=0 on host cores ({desc}); bounded sample of the {weak_shape(args.gpus)} workload"
+    wm, wn, wk = weak_shape(args.gpus)
+    cfg = workload_config(dtype, wm, wn, wk, "host CPU cores (reference arm)")
+    cfg["reference_sample"] = f"each step = one {dtype}gemm {n}x{n}x{n} NN alpha=1 beta=0 on the host cores (bounded sample of the workload above)"
     print(json.dumps({
         "impl": "reference", "metric": f"{dtype.upper()}GEMM TFLOP/s (2mnk/t)", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == "d" else dtype,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"d": "f64", "s": "f32", "z": "c128", "c": "c64", "sb": "bf16->f32"}[dtype],
         "data": "synthetic",
-        "config": {"workload": f"{dtype}gemm NN col-major {n}x{n}x{n} (bounded CPU sample)", "alpha": 1.0, "beta": 0.0},
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -269,11 +283,42 @@ def run_gpu(args):
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
     peak, peak_src = measured_peak(dtype)
     real_flops_launch = FLOP_FACTOR[dtype] * (m * n * k if world == 1 else 0)
+    # N > 1 end to end: every rank's shards start in pinned HOST memory; a step = H2D of the local A and B
+    # pieces, the SUMMA sweep, D2H of the local C piece (all ranks take part, so it runs before the
+    # rank-0-only reporting)
+    e2e_multi = None
+    if world > 1 and not args.no_e2e:
+        ha, hb = a.cpu().pin_memory(), b.cpu().pin_memory()
+        hc = torch.empty(c.shape, dtype=c.dtype).pin_memory()
+        da, db, dc = torch.empty_like(a), torch.empty_like(b), torch.empty_like(c)
+
+        def e2e_step():
+            da.copy_(ha, non_blocking=True); db.copy_(hb, non_blocking=True)
+            sm.run(1.0, da, db, 0.0, dc)
+            hc.copy_(dc, non_blocking=True)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        nst = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(nst):
+            e2e_step()
+        barrier()
+        dt_e = torch.tensor([(time.perf_counter() - t0) / nst], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        bytes_in = torch.tensor([float(ha.numel() * ha.element_size() + hb.numel() * hb.element_size())], device=dev, dtype=torch.float64)
+        bytes_out = torch.tensor([float(hc.numel() * hc.element_size())], device=dev, dtype=torch.float64)
+        dist.all_reduce(bytes_in); dist.all_reduce(bytes_out)
+        e2e_multi = {"value": flops_step / float(dt_e.item()) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(bytes_in.item()),
+                     "d2h_bytes_per_step": int(bytes_out.item()), "ms_per_step": float(dt_e.item()) * 1e3, "steps": nst,
+                     "api": "per rank: pinned host shards -> device, openblas_b200.summa.Summa.run (local product b200_gemm_async), C shard -> pinned host",
+                     "result_checksum": float(hc[::97, ::89].double().sum())}
     out = None
     if rank == 0:
         e2e = None
         if world == 1 and not args.no_e2e:
             e2e = run_e2e(ob, torch, code, dtype, m, n, k, tdt, odt, args)
+        elif world > 1:
+            e2e = e2e_multi
         cpu_b = cpu_baseline(dtype) if (world == 1 and not args.no_cpu) else None
         achieved = (real_flops_launch / (kern_ms_avg * 1e-3) / 1e12) if world == 1 else (FLOP_FACTOR[dtype] * m * n * k / world / (total_ms / args.steps * 1e-3) / 1e12)
         out = {
@@ -281,11 +326,11 @@ def run_gpu(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"d": "f64", "s": "f32", "z": "c128", "c": "c64", "sb": "bf16->f32"}[dtype], "data": "synthetic",
-            "config": {"workload": f"{dtype}gemm NN column-major {m}x{n}x{k} alpha=1 beta=0 (BASELINE configs[1] at N=1; configs[3] shape at N=8)",
-                       "parallelism": parallelism, "l2_policy": "inputs larger than L2 (A,B >= 2 GiB each vs 126 MB L2)",
-                       "inputs": "uniform(-0.5,0.5), fixed seed, resident in HBM"},
+            "config": workload_config(dtype, m, n, k, parallelism),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES.get((dtype, m, n, k)) if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         "algorithmic_bytes": (2 if dtype == "sb" else {"s": 4, "d": 8, "c": 8, "z": 16}[dtype]) * (m * k + k * n) + {"s": 4, "d": 8, "c": 8, "z": 16, "sb": 4}[dtype] * m * n,
+                         "peak_source": peak_src,
                          "kernel": ob.cblas.last_kernel(), "kernel_ms_avg": kern_ms_avg if world == 1 else None,
                          "note": "achieved = real flops of one launch (2mnk, 8mnk complex) / CUDA-event duration of that launch; per GPU at N>1"},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -54,7 +54,9 @@ static int set_error(cudaError_t e, const char *what) {
 /* One in-flight call's resources.  Contexts are pooled: at most as many exist as there were
  * concurrent callers. */
 struct Context {
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;                /* compute (and small-problem copies) */
+  cudaStream_t s_in = nullptr, s_out = nullptr; /* H2D / D2H streams of the pipelined host path */
+  std::vector<cudaEvent_t> events;
   char *dws = nullptr;  size_t dws_bytes = 0;   /* device workspace */
   char *hws = nullptr;  size_t hws_bytes = 0;   /* pinned host staging */
 };
@@ -214,6 +216,97 @@ static void pack_to(char *dst, const Operand &o) {
     memcpy(dst + (size_t)j * (size_t)o.ld_dev * o.es, o.host + (size_t)j * (size_t)o.ld_user * o.es, row_bytes);
 }
 
+/* Pipelined host path for big problems: C is cut into kPanel x kPanel blocks; row panels of
+ * op(A) and column panels of op(B) are uploaded alternately on the H2D stream, every block whose two
+ * panels have landed is multiplied on the compute stream, and finished blocks are downloaded on the
+ * D2H stream -- so after the first pair of panels the PCIe transfers in both directions hide
+ * behind the GEMMs (the reference, being a CPU library, has no such phase; this is what makes the
+ * host-pointer BLAS call approach the device-resident rate). */
+static const int64_t kPanel = 2048;
+
+static int event_at(Context *ctx, size_t i, cudaEvent_t *out) {
+  while (ctx->events.size() <= i) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->events.push_back(e);
+  }
+  *out = ctx->events[i];
+  return 0;
+}
+
+static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &g, const Operand &A,
+                         const Operand &B, const Operand &C, bool use_beta) {
+  if (!ctx->s_in) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  const int64_t pm = (p->m + kPanel - 1) / kPanel, pn = (p->n + kPanel - 1) / kPanel;
+  const size_t ies = A.es, oes = C.es;
+  const bool ta = p->transa & 1, tb = p->transb & 1;
+  cudaStream_t sc = ctx->stream, si = ctx->s_in, so = ctx->s_out;
+  size_t ev = 0;
+  std::vector<cudaEvent_t> ev_a(pm, nullptr), ev_b(pn, nullptr);
+  int err;
+
+  auto upload_a = [&](int64_t i) -> int {
+    if (A.kind == PTR_DEVICE) return 0;
+    const int64_t i0 = i * kPanel, mb = (p->m - i0 < kPanel) ? p->m - i0 : kPanel;
+    if (!ta) CK(cudaMemcpy2DAsync(A.dev + i0 * ies, A.ld_dev * ies, A.host + i0 * ies, A.ld_user * ies, mb * ies, p->k, cudaMemcpyHostToDevice, si));
+    else     CK(cudaMemcpy2DAsync(A.dev + i0 * A.ld_dev * ies, A.ld_dev * ies, A.host + i0 * A.ld_user * ies, A.ld_user * ies, p->k * ies, mb, cudaMemcpyHostToDevice, si));
+    if ((err = event_at(ctx, ev++, &ev_a[i]))) return err;
+    CK(cudaEventRecord(ev_a[i], si));
+    return 0;
+  };
+  auto upload_b = [&](int64_t j) -> int {
+    if (B.kind == PTR_DEVICE) return 0;
+    const int64_t j0 = j * kPanel, nb = (p->n - j0 < kPanel) ? p->n - j0 : kPanel;
+    if (!tb) CK(cudaMemcpy2DAsync(B.dev + j0 * B.ld_dev * ies, B.ld_dev * ies, B.host + j0 * B.ld_user * ies, B.ld_user * ies, p->k * ies, nb, cudaMemcpyHostToDevice, si));
+    else     CK(cudaMemcpy2DAsync(B.dev + j0 * ies, B.ld_dev * ies, B.host + j0 * ies, B.ld_user * ies, nb * ies, p->k, cudaMemcpyHostToDevice, si));
+    if ((err = event_at(ctx, ev++, &ev_b[j]))) return err;
+    CK(cudaEventRecord(ev_b[j], si));
+    return 0;
+  };
+  auto block = [&](int64_t i, int64_t j) -> int {
+    const int64_t i0 = i * kPanel, j0 = j * kPanel;
+    const int64_t mb = (p->m - i0 < kPanel) ? p->m - i0 : kPanel, nb = (p->n - j0 < kPanel) ? p->n - j0 : kPanel;
+    DeviceGemm b = g;
+    b.m = mb; b.n = nb;
+    b.a = A.dev + (ta ? i0 * A.ld_dev : i0) * ies;
+    b.b = B.dev + (tb ? j0 : j0 * B.ld_dev) * ies;
+    b.c = C.dev + (i0 + j0 * C.ld_dev) * oes;
+    if (C.kind != PTR_DEVICE && use_beta) {
+      cudaEvent_t e;
+      CK(cudaMemcpy2DAsync((void *)b.c, C.ld_dev * oes, C.host + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, mb * oes, nb, cudaMemcpyHostToDevice, si));
+      if ((err = event_at(ctx, ev++, &e))) return err;
+      CK(cudaEventRecord(e, si));
+      CK(cudaStreamWaitEvent(sc, e, 0));
+    }
+    if (ev_a[i]) CK(cudaStreamWaitEvent(sc, ev_a[i], 0));
+    if (ev_b[j]) CK(cudaStreamWaitEvent(sc, ev_b[j], 0));
+    CK(dispatch(b, sc));
+    if (C.kind != PTR_DEVICE) {
+      cudaEvent_t e;
+      if ((err = event_at(ctx, ev++, &e))) return err;
+      CK(cudaEventRecord(e, sc));
+      CK(cudaStreamWaitEvent(so, e, 0));
+      CK(cudaMemcpy2DAsync((char *)p->c + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, b.c, C.ld_dev * oes, mb * oes, nb, cudaMemcpyDeviceToHost, so));
+    }
+    return 0;
+  };
+
+  const int64_t steps = pm > pn ? pm : pn;
+  for (int64_t t = 0; t < steps; t++) {
+    if (t < pm && (err = upload_a(t))) return err;
+    if (t < pn && (err = upload_b(t))) return err;
+    if (t < pm) for (int64_t j = 0; j <= t && j < pn; j++) if ((err = block(t, j))) return err;   /* new row    */
+    if (t < pn) for (int64_t i = 0; i < t && i < pm; i++) if ((err = block(i, t))) return err;    /* new column */
+  }
+  CK(cudaStreamSynchronize(si));
+  CK(cudaStreamSynchronize(sc));
+  CK(cudaStreamSynchronize(so));
+  return 0;
+}
+
 static int run_on_context(Context *ctx, const b200_problem *p) {
   DeviceGemm g;
   g.dtype = p->dtype; g.transa = p->transa; g.transb = p->transb;
@@ -297,6 +390,8 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
     }
     return 0;
   }
+
+  if (product && p->m >= 2 * kPanel && p->n >= 2 * kPanel && need >= (128u << 20)) return run_pipelined(ctx, p, g, A, B, C, use_beta);
 
   /* large host operands: strided DMA straight from / to the caller's memory (full PCIe
    * rate when it is pinned; staged by the driver when it is pageable) */
