@@ -392,7 +392,7 @@ def run_sweep(args):
         for nsz in sizes:
             if dtype in ("z", "c") and nsz > 8192:
                 continue
-            ops = [(0, 0)] if nsz > 4096 else [(0, 0), (1, 0), (0, 1), (1, 1)]
+            ops = [(0, 0)] if (nsz > 4096 and not args.all_ops) else [(0, 0), (1, 0), (0, 1), (1, 1)]
             for ta, tb in ops:
                 m = n = k = nsz
                 mk = lambda: (torch.view_as_complex(torch.rand((nsz, nsz, 2), device=dev, dtype=torch.float64 if dtype == "z" else torch.float32) - 0.5)
@@ -429,6 +429,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true"); ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sweep", action="store_true"); ap.add_argument("--sizes", default="1024,2048,4096,8192,16384")
     ap.add_argument("--sweep-dtypes", default="d,s,z,c,sb")
+    ap.add_argument("--all-ops", action="store_true", help="sweep: all four N/T combinations at every size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

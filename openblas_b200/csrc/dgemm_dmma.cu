@@ -237,10 +237,10 @@ cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
  * long_scoreboard 4 % on the address registers, short_scoreboard 6 %).  Here ONE extra warp is the
  * producer: each of its lanes copies whole tile rows with the TMA engine's 1-D bulk copy
  * (cp.async.bulk, SASS UBLKCP) into the same padded, conflict-free shared layout and completion
- * is tracked by mbarriers (full[stage] with expect_tx, empty[stage] with one arrival per consumer
- * warp), so the 8 DMMA warps never execute a load instruction for global memory, never hit a
- * CTA-wide barrier in the main loop, and the producer runs ahead across C tiles (the next tile's
- * first stages are in flight during the epilogue). */
+ * is tracked by mbarriers (full[stage], empty[stage] with one arrival per consumer warp), so the
+ * 8 DMMA warps never execute a load instruction for global memory, never hit a CTA-wide barrier
+ * in the main loop, and the producers run ahead across C tiles (the next tile's first stages are in
+ * flight during the epilogue).  Two producer warps: one per operand (see produce_operand). */
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -266,14 +266,47 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void *src, uint32_
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+/* Producer for one operand tile.  mn-contiguous storage: whole 1 KB rows by bulk copy (one per lane);
+ * k-contiguous storage: rows are only BK*8 = 256 bytes and the TMA engine retires roughly one bulk
+ * copy per ~56 cycles per SM whatever its size (measured: TN, 256 such copies per stage, ran at 57 %
+ * of peak, NT with 64 copies of 1 KB at 98 %), so those tiles are fetched with 16-byte cp.async
+ * from this warp instead, completion reported to the same mbarrier (arrive.noinc). */
+template <bool MN_CONTIG, int ROWS, int BK, int LD_MN, int LD_K>
+__device__ __forceinline__ void produce_operand(uint32_t s_tile, const double *__restrict__ g, int64_t ld, int64_t mn0,
+                                                int64_t k0, uint32_t bar, int lane) {
+  if (MN_CONTIG) {
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)ROWS * BK * 8);
+    __syncwarp();
+    for (int r = lane; r < BK; r += 32)
+      bulk_copy(s_tile + (uint32_t)(r * LD_MN * 8), g + mn0 + (k0 + r) * ld, ROWS * 8, bar);
+  } else {
+    constexpr int CPR = BK / 2;                       /* 16-byte chunks per row */
+    constexpr int RSTEP = 32 / CPR;                   /* rows covered by one warp-wide copy */
+    const char *src = (const char *)(g + k0 + (lane % CPR) * 2 + (mn0 + lane / CPR) * ld);
+    uint32_t dst = s_tile + (uint32_t)(((lane / CPR) * LD_K + (lane % CPR) * 2) * 8);
+    const int64_t src_step = (int64_t)RSTEP * ld * 8;
+#pragma unroll 8
+    for (int i = 0; i < ROWS / RSTEP; i++) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      src += src_step;
+      dst += RSTEP * LD_K * 8;
+    }
+    cp_async_mbar_arrive_noinc(bar);
+  }
+}
+
 template <class C_, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(C_::THREADS + 32, 1)
+__global__ void __launch_bounds__(C_::THREADS + 64, 1)
 dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
   constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, LD_K = C_::LD_K, STAGES = C_::STAGES;
   constexpr int FM = C_::FM, FN = C_::FN;
   constexpr int LDA_MN = C_::LDA_MN, LDB_MN = C_::LDB_MN;
   constexpr int A_DOUBLES = C_::A_DOUBLES, STAGE_DOUBLES = C_::STAGE_DOUBLES;
-  constexpr uint32_t STAGE_TX = (uint32_t)(BM + BN) * BK * 8;          /* payload bytes per stage */
+  constexpr uint32_t FULL_ARRIVALS = (A_MN ? 1 : 32) + (B_MN ? 1 : 32);  /* expect_tx lane / cp.async lanes */
   extern __shared__ __align__(16) double smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t bars = smem_base + (uint32_t)(STAGES * STAGE_DOUBLES * 8);
@@ -288,13 +321,14 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
   const int64_t ktiles = g.k / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), C_::THREADS / 32); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), FULL_ARRIVALS); mbar_init(empty_bar(s), C_::THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == C_::THREADS / 32) {
-    /* =============================================================== producer warp */
+  if (warp >= C_::THREADS / 32) {
+    /* ============================== producer warps: warp 8 feeds A tiles, warp 9 feeds B tiles */
+    const bool feeds_a = warp == C_::THREADS / 32;
     int slot = 0; uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       int64_t bm, bn;
@@ -303,29 +337,16 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
       for (int64_t kt = 0; kt < ktiles; kt++) {
         const int64_t k0 = kt * BK;
         mbar_wait(empty_bar(slot), phase ^ 1);
-        if (probe_noload && kt >= STAGES) {           /* measurement probe: pure compute, stale tiles */
-          if (lane == 0) mbar_arrive(full_bar(slot));
-          __syncwarp();
-          if (++slot == STAGES) { slot = 0; phase ^= 1; }
-          continue;
-        }
-        if (lane == 0) mbar_expect_tx(full_bar(slot), STAGE_TX);
-        __syncwarp();
         const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_DOUBLES * 8), sb = sa + (uint32_t)(A_DOUBLES * 8);
-        if (A_MN) {       /* BK rows (k) of BM contiguous doubles */
-          for (int r = lane; r < BK; r += 32)
-            bulk_copy(sa + (uint32_t)(r * LDA_MN * 8), A + m0 + (k0 + r) * g.lda, BM * 8, full_bar(slot));
-        } else {          /* BM rows (m) of BK contiguous doubles */
-          for (int r = lane; r < BM; r += 32)
-            bulk_copy(sa + (uint32_t)(r * LD_K * 8), A + k0 + (m0 + r) * g.lda, BK * 8, full_bar(slot));
-        }
-        if (B_MN) {
-          for (int r = lane; r < BK; r += 32)
-            bulk_copy(sb + (uint32_t)(r * LDB_MN * 8), B + n0 + (k0 + r) * g.ldb, BN * 8, full_bar(slot));
+        if (probe_noload && kt >= STAGES) {           /* measurement probe: pure compute, stale tiles */
+          constexpr uint32_t mine_a = A_MN ? 1 : 32, mine_b = B_MN ? 1 : 32;
+          if (lane < (feeds_a ? mine_a : mine_b)) mbar_arrive(full_bar(slot));
+        } else if (feeds_a) {
+          produce_operand<A_MN, BM, BK, LDA_MN, LD_K>(sa, A, g.lda, m0, k0, full_bar(slot), lane);
         } else {
-          for (int r = lane; r < BN; r += 32)
-            bulk_copy(sb + (uint32_t)(r * LD_K * 8), B + k0 + (n0 + r) * g.ldb, BK * 8, full_bar(slot));
+          produce_operand<B_MN, BN, BK, LDB_MN, LD_K>(sb, B, g.ldb, n0, k0, full_bar(slot), lane);
         }
+        __syncwarp();
         if (++slot == STAGES) { slot = 0; phase ^= 1; }
       }
     }
@@ -411,7 +432,7 @@ cudaError_t launch_bulk_variant(const DeviceGemm &g, cudaStream_t stream) {
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   static int probe = -1;   /* B200_DGEMM_PROBE_NOLOAD=1: timing probe only, results are garbage */
   if (probe < 0) { const char *e = getenv("B200_DGEMM_PROBE_NOLOAD"); probe = e ? atoi(e) : 0; }
-  kern<<<grid, C_::THREADS + 32, smem_bytes, stream>>>(g, probe);
+  kern<<<grid, C_::THREADS + 64, smem_bytes, stream>>>(g, probe);
   return cudaGetLastError();
 }
 
