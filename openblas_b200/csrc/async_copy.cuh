@@ -185,4 +185,97 @@ struct KStager {
   __device__ __forceinline__ void advance() { src += (int64_t)BK * ES; }
 };
 
+/* ---------------------------------------------------------------------------------------------
+ * mbarrier / bulk-copy helpers and the producer-warp tile fetch shared by the DMMA kernels. */
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+/* Producer for one operand tile; every lane of the producer warp arrives once on `bar` per tile.
+ * mn-contiguous storage, interior tile: whole 1 KB rows by bulk copy (one per lane).
+ * k-contiguous storage: rows are only BK*8 = 256 bytes and the TMA engine retires roughly one bulk
+ * copy per ~56 cycles per SM whatever its size (measured: TN with 256 such copies per stage ran at
+ * 57 % of peak, NT with 64 copies of 1 KB at 98 %), so those tiles are fetched with 16-byte cp.async
+ * from this warp instead, completion reported to the same mbarrier (arrive.noinc).
+ * Edge tiles (partial in mn or in k) always use the cp.async form, whose src-size operand zero-fills
+ * what lies outside the matrix. */
+template <int ES, bool MN_CONTIG, int ROWS, int BK, int LD_MN, int LD_K>
+__device__ __forceinline__ void produce_operand(uint32_t s_tile, const void *__restrict__ gv, int64_t ld, int64_t mn0,
+                                                int64_t k0, int64_t mn_end, int64_t k_end, uint32_t bar, int lane) {
+  constexpr int VE = 16 / ES;                         /* elements per 16-byte chunk (2 doubles, 1 complex double) */
+  const char *g = (const char *)gv;
+  const int64_t mn_left = mn_end - mn0, k_left = k_end - k0;
+  const bool interior = mn_left >= ROWS && k_left >= BK;
+  if (MN_CONTIG) {
+    if (interior) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)ROWS * BK * ES); else mbar_arrive(bar);
+      __syncwarp();
+      for (int r = lane; r < BK; r += 32)
+        bulk_copy(s_tile + (uint32_t)(r * LD_MN * ES), g + (mn0 + (k0 + r) * ld) * ES, ROWS * ES, bar);
+      return;
+    }
+    constexpr int CPR = ROWS / VE;                    /* 16-byte chunks per k row */
+    for (int c = lane; c < CPR * BK; c += 32) {
+      const int k = c / CPR, mn = (c % CPR) * VE;
+      const int64_t left = (k < k_left) ? mn_left - mn : 0;
+      const int bytes = left >= VE ? 16 : (left > 0 ? (int)left * ES : 0);
+      const char *src = bytes ? g + (mn0 + mn + (k0 + k) * ld) * ES : g;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_tile + (uint32_t)((k * LD_MN + mn) * ES)), "l"(src), "r"(bytes) : "memory");
+    }
+    cp_async_mbar_arrive_noinc(bar);
+  } else {
+    constexpr int CPR = BK / VE;                      /* 16-byte chunks per row */
+    constexpr int RSTEP = 32 / CPR;                   /* rows covered by one warp-wide copy */
+    static_assert(32 % CPR == 0 && ROWS % RSTEP == 0, "k-contiguous tile does not divide over a warp");
+    const int kc = (lane % CPR) * VE, r0 = lane / CPR;
+    const char *src = g + (k0 + kc + (mn0 + r0) * ld) * ES;
+    uint32_t dst = s_tile + (uint32_t)((r0 * LD_K + kc) * ES);
+    const int64_t src_step = (int64_t)RSTEP * ld * ES;
+    if (interior) {
+#pragma unroll 8
+      for (int i = 0; i < ROWS / RSTEP; i++) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        src += src_step;
+        dst += RSTEP * LD_K * ES;
+      }
+    } else {
+      const int64_t kl = k_left - kc;
+      const int kbytes = kl >= VE ? 16 : (kl > 0 ? (int)kl * ES : 0);
+      for (int i = 0; i < ROWS / RSTEP; i++) {
+        const int bytes = (r0 + i * RSTEP < mn_left) ? kbytes : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(bytes ? src : g), "r"(bytes) : "memory");
+        src += src_step;
+        dst += RSTEP * LD_K * ES;
+      }
+    }
+    cp_async_mbar_arrive_noinc(bar);
+  }
+}
+
+
 }  // namespace b200

@@ -231,8 +231,7 @@ cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * Bulk-copy variant for interior problems (m, n multiples of the tile, k a multiple of the k step,
- * 16-byte aligned operands): the cp.async ring above costs every thread 8 LDGSTS plus their
+ * Producer-warp variant (any m, n, k; A and B columns 16-byte aligned): the cp.async ring above costs every thread 8 LDGSTS plus their
  * address registers per k tile and a CTA-wide barrier per k tile (ncu: stall_barrier 3 %,
  * long_scoreboard 4 % on the address registers, short_scoreboard 6 %).  Here ONE extra warp is the
  * producer: each of its lanes copies whole tile rows with the TMA engine's 1-D bulk copy
@@ -241,72 +240,14 @@ cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
  * 8 DMMA warps never execute a load instruction for global memory, never hit a CTA-wide barrier
  * in the main loop, and the producers run ahead across C tiles (the next tile's first stages are in
  * flight during the epilogue).  Two producer warps: one per operand (see produce_operand). */
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-/* Producer for one operand tile.  mn-contiguous storage: whole 1 KB rows by bulk copy (one per lane);
- * k-contiguous storage: rows are only BK*8 = 256 bytes and the TMA engine retires roughly one bulk
- * copy per ~56 cycles per SM whatever its size (measured: TN, 256 such copies per stage, ran at 57 %
- * of peak, NT with 64 copies of 1 KB at 98 %), so those tiles are fetched with 16-byte cp.async
- * from this warp instead, completion reported to the same mbarrier (arrive.noinc). */
-template <bool MN_CONTIG, int ROWS, int BK, int LD_MN, int LD_K>
-__device__ __forceinline__ void produce_operand(uint32_t s_tile, const double *__restrict__ g, int64_t ld, int64_t mn0,
-                                                int64_t k0, uint32_t bar, int lane) {
-  if (MN_CONTIG) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)ROWS * BK * 8);
-    __syncwarp();
-    for (int r = lane; r < BK; r += 32)
-      bulk_copy(s_tile + (uint32_t)(r * LD_MN * 8), g + mn0 + (k0 + r) * ld, ROWS * 8, bar);
-  } else {
-    constexpr int CPR = BK / 2;                       /* 16-byte chunks per row */
-    constexpr int RSTEP = 32 / CPR;                   /* rows covered by one warp-wide copy */
-    const char *src = (const char *)(g + k0 + (lane % CPR) * 2 + (mn0 + lane / CPR) * ld);
-    uint32_t dst = s_tile + (uint32_t)(((lane / CPR) * LD_K + (lane % CPR) * 2) * 8);
-    const int64_t src_step = (int64_t)RSTEP * ld * 8;
-#pragma unroll 8
-    for (int i = 0; i < ROWS / RSTEP; i++) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      src += src_step;
-      dst += RSTEP * LD_K * 8;
-    }
-    cp_async_mbar_arrive_noinc(bar);
-  }
-}
-
 template <class C_, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(C_::THREADS + 64, 1)
-dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
+dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
   constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, LD_K = C_::LD_K, STAGES = C_::STAGES;
   constexpr int FM = C_::FM, FN = C_::FN;
   constexpr int LDA_MN = C_::LDA_MN, LDB_MN = C_::LDB_MN;
   constexpr int A_DOUBLES = C_::A_DOUBLES, STAGE_DOUBLES = C_::STAGE_DOUBLES;
-  constexpr uint32_t FULL_ARRIVALS = (A_MN ? 1 : 32) + (B_MN ? 1 : 32);  /* expect_tx lane / cp.async lanes */
+  constexpr uint32_t FULL_ARRIVALS = 64;   /* every lane of both producer warps arrives once per stage */
   extern __shared__ __align__(16) double smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t bars = smem_base + (uint32_t)(STAGES * STAGE_DOUBLES * 8);
@@ -317,8 +258,8 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
   const double *__restrict__ B = (const double *)g.b;
   double *__restrict__ C = (double *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tiles_m = g.m / BM, tiles_n = g.n / BN, tiles = tiles_m * tiles_n;
-  const int64_t ktiles = g.k / BK;
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const int64_t ktiles = (g.k + BK - 1) / BK;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), FULL_ARRIVALS); mbar_init(empty_bar(s), C_::THREADS / 32); }
@@ -339,12 +280,11 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
         mbar_wait(empty_bar(slot), phase ^ 1);
         const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_DOUBLES * 8), sb = sa + (uint32_t)(A_DOUBLES * 8);
         if (probe_noload && kt >= STAGES) {           /* measurement probe: pure compute, stale tiles */
-          constexpr uint32_t mine_a = A_MN ? 1 : 32, mine_b = B_MN ? 1 : 32;
-          if (lane < (feeds_a ? mine_a : mine_b)) mbar_arrive(full_bar(slot));
+          mbar_arrive(full_bar(slot));
         } else if (feeds_a) {
-          produce_operand<A_MN, BM, BK, LDA_MN, LD_K>(sa, A, g.lda, m0, k0, full_bar(slot), lane);
+          produce_operand<8, A_MN, BM, BK, LDA_MN, LD_K>(sa, A, g.lda, m0, k0, g.m, g.k, full_bar(slot), lane);
         } else {
-          produce_operand<B_MN, BN, BK, LDB_MN, LD_K>(sb, B, g.ldb, n0, k0, full_bar(slot), lane);
+          produce_operand<8, B_MN, BN, BK, LDB_MN, LD_K>(sb, B, g.ldb, n0, k0, g.n, g.k, full_bar(slot), lane);
         }
         __syncwarp();
         if (++slot == STAGES) { slot = 0; phase ^= 1; }
@@ -398,20 +338,31 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int probe_noload) {
       if (++slot == STAGES) { slot = 0; phase ^= 1; }
     }
 
-    /* epilogue (interior tile: no bounds checks; 16-byte stores need ldc even, C 16-byte aligned) */
+    /* epilogue: lane owns C[m .. m+1][n]; 16-byte stores when ldc is even and C 16-byte aligned */
 #pragma unroll
     for (int j = 0; j < FN; j++) {
       const int64_t n = n0 + wn + 8 * j + fi;
+      if (n >= g.n) continue;
 #pragma unroll
       for (int i = 0; i < FM; i++) {
         const int64_t m = m0 + wm + 8 * i + 2 * fk;
+        if (m >= g.m) continue;
         double *p = C + m + n * g.ldc;
         double r0 = alpha * acc[i][j][0], r1 = alpha * acc[i][j][1];
-        if (use_beta) {
-          double2 old = *reinterpret_cast<const double2 *>(p);
-          r0 = fma(beta, old.x, r0); r1 = fma(beta, old.y, r1);
+        if (vec_c && m + 1 < g.m) {
+          if (use_beta) {
+            double2 old = *reinterpret_cast<const double2 *>(p);
+            r0 = fma(beta, old.x, r0); r1 = fma(beta, old.y, r1);
+          }
+          *reinterpret_cast<double2 *>(p) = make_double2(r0, r1);
+        } else {
+          if (use_beta) r0 = fma(beta, p[0], r0);
+          p[0] = r0;
+          if (m + 1 < g.m) {
+            if (use_beta) r1 = fma(beta, p[1], r1);
+            p[1] = r1;
+          }
         }
-        *reinterpret_cast<double2 *>(p) = make_double2(r0, r1);
       }
     }
   }
@@ -428,18 +379,19 @@ cudaError_t launch_bulk_variant(const DeviceGemm &g, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int64_t tiles = (g.m / C_::BM) * (g.n / C_::BN);
+  int64_t tiles = ((g.m + C_::BM - 1) / C_::BM) * ((g.n + C_::BN - 1) / C_::BN);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
   static int probe = -1;   /* B200_DGEMM_PROBE_NOLOAD=1: timing probe only, results are garbage */
   if (probe < 0) { const char *e = getenv("B200_DGEMM_PROBE_NOLOAD"); probe = e ? atoi(e) : 0; }
-  kern<<<grid, C_::THREADS + 64, smem_bytes, stream>>>(g, probe);
+  kern<<<grid, C_::THREADS + 64, smem_bytes, stream>>>(g, vec_c, probe);
   return cudaGetLastError();
 }
 
+/* the producer-warp kernel needs 16-byte aligned A and B columns; any m, n, k */
 template <class C_>
 bool bulk_eligible(const DeviceGemm &g) {
-  return g.m % C_::BM == 0 && g.n % C_::BN == 0 && g.k % C_::BK == 0 && g.lda % 2 == 0 && g.ldb % 2 == 0 &&
-         g.ldc % 2 == 0 && ((((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 15) == 0);
+  return g.lda % 2 == 0 && g.ldb % 2 == 0 && ((((uintptr_t)g.a | (uintptr_t)g.b) & 15) == 0);
 }
 
 template <class C_>

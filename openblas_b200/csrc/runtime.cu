@@ -326,6 +326,11 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
   B.kind = product ? classify(p->b) : PTR_DEVICE;
   C.kind = classify(p->c);
 
+  /* The BLAS call is synchronous and works on "the operands as of now".  A device-resident operand may
+   * still be being produced by work the caller queued on its own streams (our streams are
+   * non-blocking, so nothing orders us after it implicitly): wait for the device first. */
+  if ((product && (A.kind == PTR_DEVICE || B.kind == PTR_DEVICE)) || C.kind == PTR_DEVICE) CK(cudaDeviceSynchronize());
+
   Operand *ops[3] = {&A, &B, &C};
   const void *user[3] = {p->a, p->b, p->c};
   size_t need = 0;

@@ -22,6 +22,7 @@
  */
 #include "gemm_common.cuh"
 #include "async_copy.cuh"
+#include <cstdlib>
 
 namespace b200 {
 namespace {
@@ -168,6 +169,163 @@ zgemm_dmma_kernel(DeviceGemm g) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Producer-warp variant (the default): same structure as dgemm_dmma.cu's -- two producer warps
+ * (one per operand: bulk copies for mn-contiguous tiles, cp.async for k-contiguous and edge tiles,
+ * both reporting to full[stage] mbarriers) feed 8 consumer warps that only execute LDS + DMMA and
+ * release stages through empty[stage]; no CTA-wide barrier in the main loop.  k step 16
+ * (k-contiguous rows of 256 bytes), 3 stages. */
+namespace pw {
+constexpr int BK = 16, STAGES = 3;
+constexpr int LDA_MN = BM + 2, LDB_MN = BN + 2, LD_K = BK + 4;                /* = 2 mod 8 / = 4 mod 8 */
+constexpr int A_ELEMS = (BK * LDA_MN > BM * LD_K) ? BK * LDA_MN : BM * LD_K;   /* 1280 */
+constexpr int B_ELEMS = (BK * LDB_MN > BN * LD_K) ? BK * LDB_MN : BN * LD_K;   /* 2560 */
+constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double2) + 64;   /* 180 KB + barriers */
+static_assert(SMEM_BYTES <= 227 * 1024, "ring does not fit");
+}  // namespace pw
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS + 64, 1)
+zgemm_dmma_pw_kernel(DeviceGemm g) {
+  constexpr int BK = pw::BK, STAGES = pw::STAGES, LDA_MN = pw::LDA_MN, LDB_MN = pw::LDB_MN, LD_K = pw::LD_K;
+  constexpr int A_ELEMS = pw::A_ELEMS, STAGE_ELEMS = pw::STAGE_ELEMS;
+  extern __shared__ __align__(16) double2 zsmem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(zsmem);
+  const uint32_t bars = smem_base + (uint32_t)(STAGES * STAGE_ELEMS * 16);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const double2 *__restrict__ A = (const double2 *)g.a;
+  const double2 *__restrict__ B = (const double2 *)g.b;
+  double2 *__restrict__ C = (double2 *)g.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const int64_t ktiles = (g.k + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 64); mbar_init(empty_bar(s), THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= THREADS / 32) {
+    const bool feeds_a = warp == THREADS / 32;
+    int slot = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      int64_t bm, bn;
+      banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+      const int64_t m0 = bm * BM, n0 = bn * BN;
+      for (int64_t kt = 0; kt < ktiles; kt++) {
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_ELEMS * 16), sb = sa + (uint32_t)(A_ELEMS * 16);
+        if (feeds_a) produce_operand<16, A_MN, BM, BK, LDA_MN, LD_K>(sa, A, g.lda, m0, kt * BK, g.m, g.k, full_bar(slot), lane);
+        else         produce_operand<16, B_MN, BN, BK, LDB_MN, LD_K>(sb, B, g.ldb, n0, kt * BK, g.n, g.k, full_bar(slot), lane);
+        __syncwarp();
+        if (++slot == STAGES) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+  const int fi = lane >> 2, fk = lane & 3;
+  const int flip_a = (g.transa & 2) ? (int)0x80000000 : 0;
+  const int flip_b = (g.transb & 2) ? (int)0x80000000 : 0;
+  const int a_off = A_MN ? (fk * LDA_MN + wm + fi) : ((wm + fi) * LD_K + fk);
+  const int b_off = B_MN ? (fk * LDB_MN + wn + fi) : ((wn + fi) * LD_K + fk);
+  constexpr int A_MT = A_MN ? 8 : 8 * LD_K;
+  constexpr int B_NT = B_MN ? 8 : 8 * LD_K;
+  constexpr int A_K4 = A_MN ? 4 * LDA_MN : 4;
+  constexpr int B_K4 = B_MN ? 4 * LDB_MN : 4;
+
+  int slot = 0; uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    int64_t bm, bn;
+    banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+    const int64_t m0 = bm * BM, n0 = bn * BN;
+
+    double re[4][4][2], im[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) re[i][j][0] = re[i][j][1] = im[i][j][0] = im[i][j][1] = 0.0;
+
+    for (int64_t kt = 0; kt < ktiles; kt++) {
+      mbar_wait(full_bar(slot), phase);
+      const double2 *sa = zsmem + slot * STAGE_ELEMS + a_off;
+      const double2 *sb = zsmem + slot * STAGE_ELEMS + A_ELEMS + b_off;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; k4++) {
+        double ar[4], ai[4], nai[4], br[4], bi[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double2 v = sa[k4 * A_K4 + i * A_MT];
+          ar[i] = v.x; ai[i] = xor_sign(v.y, flip_a); nai[i] = xor_sign(ai[i], (int)0x80000000);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double2 v = sb[k4 * B_K4 + j * B_NT];
+          br[j] = v.x; bi[j] = xor_sign(v.y, flip_b);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            dmma884(re[i][j][0], re[i][j][1], br[j], ar[i]);
+            dmma884(im[i][j][0], im[i][j][1], bi[j], ar[i]);
+            dmma884(re[i][j][0], re[i][j][1], bi[j], nai[i]);
+            dmma884(im[i][j][0], im[i][j][1], br[j], ai[i]);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(slot));
+      if (++slot == STAGES) { slot = 0; phase ^= 1; }
+    }
+
+    const double alr = g.alpha_re, ali = g.alpha_im, ber = g.beta_re, bei = g.beta_im;
+    const bool use_beta = !(ber == 0.0 && bei == 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t n = n0 + wn + 8 * j + fi;
+      if (n >= g.n) continue;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int64_t m = m0 + wm + 8 * i + 2 * fk + h;
+          if (m >= g.m) continue;
+          double2 *p = C + m + n * g.ldc;
+          double xr = re[i][j][h], xi = im[i][j][h];
+          double2 out;
+          out.x = alr * xr - ali * xi;
+          out.y = alr * xi + ali * xr;
+          if (use_beta) {
+            double2 old = *p;
+            out.x += ber * old.x - bei * old.y;
+            out.y += ber * old.y + bei * old.x;
+          }
+          *p = out;
+        }
+      }
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+cudaError_t launch_pw_variant(const DeviceGemm &g, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = zgemm_dmma_pw_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t tiles = ((g.m + BM - 1) / BM) * ((g.n + BN - 1) / BN);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, THREADS + 64, pw::SMEM_BYTES, stream>>>(g);
+  return cudaGetLastError();
+}
+
 template <bool A_MN, bool B_MN>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream) {
   static bool configured = false;
@@ -190,7 +348,17 @@ cudaError_t launch_zgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   /* one complex = one 16-byte cp.async: needs 16-byte aligned bases (any ld) */
   if (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 15) return cudaErrorNotSupported;
   const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  static int cfg = -1;
+  if (cfg < 0) { const char *ev = getenv("B200_ZGEMM_CFG"); cfg = ev ? atoi(ev) : 1; }
   cudaError_t e;
+  if (cfg == 1) {
+    if (a_mn && b_mn) e = launch_pw_variant<true, true>(g, stream);
+    else if (a_mn && !b_mn) e = launch_pw_variant<true, false>(g, stream);
+    else if (!a_mn && b_mn) e = launch_pw_variant<false, true>(g, stream);
+    else e = launch_pw_variant<false, false>(g, stream);
+    if (e == cudaSuccess) count_launch("zgemm_dmma_pw_64x128x16");
+    return e;
+  }
   if (a_mn && b_mn) e = launch_variant<true, true>(g, stream);
   else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream);
   else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream);
