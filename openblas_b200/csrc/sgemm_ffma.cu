@@ -217,6 +217,210 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Producer-warp variant (B200_SGEMM_CFG=1; NOT the default: measured 43-47 TFLOP/s against 57 for the
+ * kernel above -- with 12 consumer warps the LDS.128 wavefronts, ~3.4 per load, become the limiter).
+ * Kept as the starting point for a larger register tile.  ncu on the kernel above: the FMA pipe is the busiest unit but
+ * only ~77 % active -- the rest goes to barrier phases, LDS waits and the loader's integer work,
+ * which shares the FMA pipe (IMAD).  Here 12 consumer warps (3 x 4, warp tile 64 x 32, 8x8 outputs per
+ * thread -> 192 x 128 x 16 CTA tile) execute nothing but LDS.128 + FFMA2, with the next k step's
+ * fragments prefetched into registers; two producer warps (A tiles / B tiles) fill a 4-stage ring
+ * with cp.async -- 16-byte copies for operands stored mn-contiguous, 4-byte TRANSPOSING copies
+ * (global k-contiguous -> shared S[k][mn]) for operands stored k-contiguous, so op() is still
+ * absorbed in the load path -- and signal full[stage] mbarriers (cp.async.mbarrier.arrive.noinc);
+ * consumers release stages through empty[stage].  No CTA-wide barrier in the main loop, any
+ * m, n, k, any 4-byte aligned operands (zero fill at the edges via the cp.async src-size). */
+namespace pw {
+constexpr int BM = 192, BN = 128, BK = 16, STAGES = 4;
+constexpr int CONSUMER_WARPS = 12, THREADS = (CONSUMER_WARPS + 4) * 32;   /* 2 producers + 2 idle: 128 regs each */
+constexpr int LDA = BM + 4, LDB = BN + 4;                                /* floats; 16-byte multiples */
+constexpr int A_FLOATS = BK * LDA, B_FLOATS = BK * LDB, STAGE_FLOATS = A_FLOATS + B_FLOATS;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * 4 + 64;
+}  // namespace pw
+
+/* one operand tile (ROWS mn x 16 k floats) -> S[k][mn]; every lane arrives once on `bar` */
+template <bool MN_CONTIG, int ROWS, int LD>
+__device__ __forceinline__ void sgemm_produce(uint32_t s_tile, const float *__restrict__ g, int64_t ld, int64_t mn0,
+                                              int64_t k0, int64_t mn_end, int64_t k_end, bool vec, uint32_t bar, int lane) {
+  constexpr int BK = pw::BK;
+  const int64_t mn_left = mn_end - mn0, k_left = k_end - k0;
+  if (MN_CONTIG && vec) {
+    constexpr int CPR = ROWS / 4;                       /* 16-byte chunks per k row */
+    for (int c = lane; c < CPR * BK; c += 32) {
+      const int k = c / CPR, mn = (c % CPR) * 4;
+      const int64_t left = (k < k_left) ? mn_left - mn : 0;
+      const int bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+      const float *src = bytes ? g + mn0 + mn + (k0 + k) * ld : g;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_tile + (uint32_t)((k * LD + mn) * 4)), "l"(src), "r"(bytes) : "memory");
+    }
+  } else if (MN_CONTIG) {
+    for (int c = lane; c < ROWS * BK; c += 32) {
+      const int k = c / ROWS, mn = c % ROWS;
+      const int bytes = (k < k_left && mn < mn_left) ? 4 : 0;
+      const float *src = bytes ? g + mn0 + mn + (k0 + k) * ld : g;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s_tile + (uint32_t)((k * LD + mn) * 4)), "l"(src), "r"(bytes) : "memory");
+    }
+  } else {
+    /* k-contiguous in memory: lanes walk k (64 contiguous bytes per mn row), 2 rows per warp copy;
+     * the 4-byte copy lands transposed at S[k][mn] */
+    const int k = lane % BK, r0 = lane / BK;
+    const float *src = g + k0 + k + (mn0 + r0) * ld;
+    uint32_t dst = s_tile + (uint32_t)((k * LD + r0) * 4);
+    const int64_t src_step = 2 * ld;
+    const bool k_ok = k < k_left;
+#pragma unroll 8
+    for (int i = 0; i < ROWS / 2; i++) {
+      const int bytes = (k_ok && r0 + 2 * i < mn_left) ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(bytes ? src : g), "r"(bytes) : "memory");
+      src += src_step;
+      dst += 8;
+    }
+  }
+  cp_async_mbar_arrive_noinc(bar);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(pw::THREADS, 1)
+sgemm_ffma_pw_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
+  constexpr int BM = pw::BM, BN = pw::BN, BK = pw::BK, STAGES = pw::STAGES, LDA = pw::LDA, LDB = pw::LDB;
+  constexpr int A_FLOATS = pw::A_FLOATS, STAGE_FLOATS = pw::STAGE_FLOATS;
+  extern __shared__ __align__(16) float fsmem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fsmem);
+  const uint32_t bars = smem_base + (uint32_t)(STAGES * STAGE_FLOATS * 4);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const float *__restrict__ A = (const float *)g.a;
+  const float *__restrict__ B = (const float *)g.b;
+  float *__restrict__ C = (float *)g.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const int64_t ktiles = (g.k + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 64); mbar_init(empty_bar(s), pw::CONSUMER_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= pw::CONSUMER_WARPS) {
+    if (warp >= pw::CONSUMER_WARPS + 2) return;          /* padding warps: only there for the register budget */
+    const bool feeds_a = warp == pw::CONSUMER_WARPS;
+    int slot = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      int64_t bm, bn;
+      banded_tile_coords<12>(t, tiles_m, tiles_n, bm, bn);
+      const int64_t m0 = bm * BM, n0 = bn * BN;
+      for (int64_t kt = 0; kt < ktiles; kt++) {
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_FLOATS * 4), sb = sa + (uint32_t)(A_FLOATS * 4);
+        if (feeds_a) sgemm_produce<A_MN, BM, LDA>(sa, A, g.lda, m0, kt * BK, g.m, g.k, vec_a, full_bar(slot), lane);
+        else         sgemm_produce<B_MN, BN, LDB>(sb, B, g.ldb, n0, kt * BK, g.n, g.k, vec_b, full_bar(slot), lane);
+        __syncwarp();
+        if (++slot == STAGES) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  /* consumers: warp grid 3 (m) x 4 (n), lanes 8 (m) x 4 (n) */
+  const int wm = (warp % 3) * 64, wn = (warp / 3) * 32;
+  const int lm = lane & 7, ln = lane >> 3;
+  const int a_off = wm + lm * 4, b_off = wn + ln * 4;     /* rows a_off..+3 and a_off+32..+35; cols b_off..+3, b_off+16..+19 */
+  const float alpha = (float)g.alpha_re, beta = (float)g.beta_re;
+  const bool use_beta = beta != 0.f;
+
+  int slot = 0; uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    int64_t bm, bn;
+    banded_tile_coords<12>(t, tiles_m, tiles_n, bm, bn);
+    const int64_t m0 = bm * BM, n0 = bn * BN;
+
+    u64 acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[p][j] = 0ull;
+
+    for (int64_t kt = 0; kt < ktiles; kt++) {
+      mbar_wait(full_bar(slot), phase);
+      const float *sa = fsmem + slot * STAGE_FLOATS + a_off;
+      const float *sb = fsmem + slot * STAGE_FLOATS + A_FLOATS + b_off;
+      ulonglong2 a_lo = *reinterpret_cast<const ulonglong2 *>(sa);
+      ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + 32);
+      float4 b_lo = *reinterpret_cast<const float4 *>(sb);
+      float4 b_hi = *reinterpret_cast<const float4 *>(sb + 16);
+#pragma unroll
+      for (int k = 0; k < BK; k++) {
+        const u64 ap[4] = {a_lo.x, a_lo.y, a_hi.x, a_hi.y};
+        const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+        if (k + 1 < BK) {                                  /* prefetch the next k step's fragments */
+          a_lo = *reinterpret_cast<const ulonglong2 *>(sa + (k + 1) * LDA);
+          a_hi = *reinterpret_cast<const ulonglong2 *>(sa + (k + 1) * LDA + 32);
+          b_lo = *reinterpret_cast<const float4 *>(sb + (k + 1) * LDB);
+          b_hi = *reinterpret_cast<const float4 *>(sb + (k + 1) * LDB + 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const u64 bb = pack2(bv[j], bv[j]);
+#pragma unroll
+          for (int p = 0; p < 4; p++) ffma2(acc[p][j], ap[p], bb);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(slot));
+      if (++slot == STAGES) { slot = 0; phase ^= 1; }
+    }
+
+    /* epilogue: column j -> n, row quad h -> m */
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int64_t n = n0 + b_off + (j < 4 ? j : 16 + (j - 4));
+      if (n >= g.n) continue;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int64_t m = m0 + a_off + h * 32;
+        if (m >= g.m) continue;
+        float v[4];
+        unpack2(acc[2 * h][j], v[0], v[1]);
+        unpack2(acc[2 * h + 1][j], v[2], v[3]);
+        float *p = C + m + n * g.ldc;
+        if (vec_c && m + 3 < g.m) {
+          float4 o = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
+          if (use_beta) {
+            float4 old = *reinterpret_cast<const float4 *>(p);
+            o.x = fmaf(beta, old.x, o.x); o.y = fmaf(beta, old.y, o.y);
+            o.z = fmaf(beta, old.z, o.z); o.w = fmaf(beta, old.w, o.w);
+          }
+          *reinterpret_cast<float4 *>(p) = o;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (m + e >= g.m) break;
+            float o = alpha * v[e];
+            if (use_beta) o = fmaf(beta, p[e], o);
+            p[e] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+cudaError_t launch_pw_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
+  static bool configured = false;
+  auto kern = sgemm_ffma_pw_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t tiles = ((g.m + pw::BM - 1) / pw::BM) * ((g.n + pw::BN - 1) / pw::BN);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, pw::THREADS, pw::SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
+  return cudaGetLastError();
+}
+
 template <bool A_MN, bool B_MN, bool PACKED>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
   static bool configured = false;
@@ -242,9 +446,18 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   const int vec_a = (((uintptr_t)g.a & 15) == 0) && (g.lda % 4 == 0);
   const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 4 == 0);
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
-  static int packed = -1;
+  static int packed = -1, cfg = -1;
   if (packed < 0) { const char *ev = getenv("B200_SGEMM_PACKED"); packed = ev ? atoi(ev) : 1; }
+  if (cfg < 0) { const char *ev = getenv("B200_SGEMM_CFG"); cfg = ev ? atoi(ev) : 0; }
   cudaError_t e;
+  if (cfg == 1) {
+    if (a_mn && b_mn) e = launch_pw_variant<true, true>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_pw_variant<true, false>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_pw_variant<false, true>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_pw_variant<false, false>(g, stream, vec_a, vec_b, vec_c);
+    if (e == cudaSuccess) count_launch("sgemm_ffma2_pw_192x128x16");
+    return e;
+  }
   if (packed) {
     if (a_mn && b_mn) e = launch_variant<true, true, true>(g, stream, vec_a, vec_b, vec_c);
     else if (a_mn && !b_mn) e = launch_variant<true, false, true>(g, stream, vec_a, vec_b, vec_c);
