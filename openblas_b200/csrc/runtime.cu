@@ -222,7 +222,12 @@ static void pack_to(char *dst, const Operand &o) {
  * D2H stream -- so after the first pair of panels the PCIe transfers in both directions hide
  * behind the GEMMs (the reference, being a CPU library, has no such phase; this is what makes the
  * host-pointer BLAS call approach the device-resident rate). */
-static const int64_t kPanel = 2048;
+static const int64_t kPanelMin = 2048;   /* smallest block edge; see panel_edge() */
+
+/* Block edge of the pipeline: 2048 gives the earliest start (first A and B panels are small) but a
+ * 2048 x 2048 block is only 256 C tiles = 1.7 waves of 148 CTAs (86 % efficient); 4096 gives 1024 tiles
+ * = 6.9 waves.  Use the larger block once the problem has enough of them to keep the pipe busy. */
+static int64_t panel_edge(int64_t m, int64_t n) { return (m >= 8192 && n >= 8192) ? 4096 : 2048; }
 
 static int event_at(Context *ctx, size_t i, cudaEvent_t *out) {
   while (ctx->events.size() <= i) {
@@ -240,6 +245,7 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
     CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
   }
+  const int64_t kPanel = panel_edge(p->m, p->n);
   const int64_t pm = (p->m + kPanel - 1) / kPanel, pn = (p->n + kPanel - 1) / kPanel;
   const size_t ies = A.es, oes = C.es;
   const bool ta = p->transa & 1, tb = p->transb & 1;
@@ -396,7 +402,7 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
     return 0;
   }
 
-  if (product && p->m >= 2 * kPanel && p->n >= 2 * kPanel && need >= (128u << 20)) return run_pipelined(ctx, p, g, A, B, C, use_beta);
+  if (product && p->m >= 2 * kPanelMin && p->n >= 2 * kPanelMin && need >= (128u << 20)) return run_pipelined(ctx, p, g, A, B, C, use_beta);
 
   /* large host operands: strided DMA straight from / to the caller's memory (full PCIe
    * rate when it is pinned; staged by the driver when it is pageable) */

@@ -60,7 +60,7 @@ __device__ __noinline__ void load_mn_unaligned(float *s, const float *__restrict
 }
 
 /* PACKED: accumulate with FFMA2 (fma.rn.f32x2) on row pairs; otherwise with scalar FFMA. */
-template <bool A_MN, bool B_MN, bool PACKED>
+template <bool A_MN, bool B_MN, int PACKED>
 __global__ void __launch_bounds__(THREADS, 2)
 sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   extern __shared__ __align__(16) float fsmem[];
@@ -155,11 +155,18 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
           ulonglong2 a_lo = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS);
           ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS + 64);
           u64 ap[4] = {a_lo.x, a_lo.y, a_hi.x, a_hi.y};
+          if (PACKED == 2) {        /* row pair outer: the 64-bit A operand is the one kept in the reuse cache */
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            u64 bb = pack2(bv[j], bv[j]);
+            for (int p = 0; p < 4; p++)
 #pragma unroll
-            for (int p = 0; p < 4; p++) ffma2(acc[p][j], ap[p], bb);
+              for (int j = 0; j < 8; j++) ffma2(acc[p][j], ap[p], pack2(bv[j], bv[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              u64 bb = pack2(bv[j], bv[j]);
+#pragma unroll
+              for (int p = 0; p < 4; p++) ffma2(acc[p][j], ap[p], bb);
+            }
           }
         } else {
           float4 a_lo = *reinterpret_cast<const float4 *>(sa + k * LDS);
@@ -421,7 +428,7 @@ cudaError_t launch_pw_variant(const DeviceGemm &g, cudaStream_t stream, int vec_
   return cudaGetLastError();
 }
 
-template <bool A_MN, bool B_MN, bool PACKED>
+template <bool A_MN, bool B_MN, int PACKED>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
   static bool configured = false;
   auto kern = sgemm_ffma_kernel<A_MN, B_MN, PACKED>;
@@ -458,16 +465,21 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
     if (e == cudaSuccess) count_launch("sgemm_ffma2_pw_192x128x16");
     return e;
   }
-  if (packed) {
-    if (a_mn && b_mn) e = launch_variant<true, true, true>(g, stream, vec_a, vec_b, vec_c);
-    else if (a_mn && !b_mn) e = launch_variant<true, false, true>(g, stream, vec_a, vec_b, vec_c);
-    else if (!a_mn && b_mn) e = launch_variant<false, true, true>(g, stream, vec_a, vec_b, vec_c);
-    else e = launch_variant<false, false, true>(g, stream, vec_a, vec_b, vec_c);
+  if (packed == 2) {
+    if (a_mn && b_mn) e = launch_variant<true, true, 2>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_variant<true, false, 2>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_variant<false, true, 2>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_variant<false, false, 2>(g, stream, vec_a, vec_b, vec_c);
+  } else if (packed) {
+    if (a_mn && b_mn) e = launch_variant<true, true, 1>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_variant<true, false, 1>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_variant<false, true, 1>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_variant<false, false, 1>(g, stream, vec_a, vec_b, vec_c);
   } else {
-    if (a_mn && b_mn) e = launch_variant<true, true, false>(g, stream, vec_a, vec_b, vec_c);
-    else if (a_mn && !b_mn) e = launch_variant<true, false, false>(g, stream, vec_a, vec_b, vec_c);
-    else if (!a_mn && b_mn) e = launch_variant<false, true, false>(g, stream, vec_a, vec_b, vec_c);
-    else e = launch_variant<false, false, false>(g, stream, vec_a, vec_b, vec_c);
+    if (a_mn && b_mn) e = launch_variant<true, true, 0>(g, stream, vec_a, vec_b, vec_c);
+    else if (a_mn && !b_mn) e = launch_variant<true, false, 0>(g, stream, vec_a, vec_b, vec_c);
+    else if (!a_mn && b_mn) e = launch_variant<false, true, 0>(g, stream, vec_a, vec_b, vec_c);
+    else e = launch_variant<false, false, 0>(g, stream, vec_a, vec_b, vec_c);
   }
   if (e == cudaSuccess) count_launch(packed ? "sgemm_ffma2_128x128x16" : "sgemm_ffma_128x128x16");
   return e;
