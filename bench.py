@@ -393,6 +393,8 @@ def run_sweep(args):
             if dtype in ("z", "c") and nsz > 8192:
                 continue
             ops = [(0, 0)] if (nsz > 4096 and not args.all_ops) else [(0, 0), (1, 0), (0, 1), (1, 1)]
+            if args.all_ops and dtype in ("z", "c"):       # BASELINE config 5: every N/T/C combination
+                ops = [(x, y) for y in (0, 1, 3) for x in (0, 1, 3)]
             for ta, tb in ops:
                 m = n = k = nsz
                 mk = lambda: (torch.view_as_complex(torch.rand((nsz, nsz, 2), device=dev, dtype=torch.float64 if dtype == "z" else torch.float32) - 0.5)
@@ -408,7 +410,7 @@ def run_sweep(args):
                 e0.record(); [f() for _ in range(reps)]; e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
                 tf = FLOP_FACTOR[dtype] * nsz ** 3 / (ms * 1e-3) / 1e12
-                rows.append({"dtype": dtype, "n": nsz, "op": "NT"[ta] + "NT"[tb], "ms": ms, "tflops_real": tf, "frac_of_peak": tf / peak,
+                rows.append({"dtype": dtype, "n": nsz, "op": "NTRC"[ta] + "NTRC"[tb], "ms": ms, "tflops_real": tf, "frac_of_peak": tf / peak,
                              "kernel": ob.cblas.last_kernel()})
                 print(json.dumps(rows[-1]), flush=True)
                 del a, b, c
