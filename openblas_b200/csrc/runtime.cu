@@ -16,6 +16,9 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <thread>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +62,15 @@ struct Context {
   std::vector<cudaEvent_t> events;
   char *dws = nullptr;  size_t dws_bytes = 0;   /* device workspace */
   char *hws = nullptr;  size_t hws_bytes = 0;   /* pinned host staging */
+  /* pinned slot rings for PAGEABLE operands of big problems (see h2d_any / d2h_any) */
+  static const int kSlots = 3;
+  char *in_slot[kSlots] = {nullptr, nullptr, nullptr};
+  char *out_slot[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t in_ev[kSlots], out_ev[kSlots];
+  bool in_busy[kSlots] = {false, false, false};
+  int in_next = 0, out_next = 0;
+  struct PendingOut { bool active = false; char *host; size_t hpitch, width, cols; };
+  PendingOut out_pending[kSlots];
 };
 static std::vector<Context *> g_free_ctx;
 
@@ -216,6 +228,148 @@ static void pack_to(char *dst, const Operand &o) {
     memcpy(dst + (size_t)j * (size_t)o.ld_dev * o.es, o.host + (size_t)j * (size_t)o.ld_user * o.es, row_bytes);
 }
 
+/* ---------------------------------------------------------------- pageable host operands
+ * BLAS callers hand us malloc'd memory.  A cudaMemcpy from pageable memory is staged by the driver
+ * at a few GB/s on one thread; instead the columns are copied into pinned slots by a small pool of
+ * host threads (the reference uses all cores for the GEMM itself; we only borrow a few for memcpy)
+ * while the previous slot is in flight on the DMA engine. */
+static const size_t kSlotBytes = 32u << 20;
+
+class HostPool {
+ public:
+  static HostPool &get() { static HostPool *p = new HostPool(); return *p; }   /* leaked on purpose: no join at exit */
+  /* run fn(i) for i in [0, n) on the pool plus the calling thread */
+  void parallel_for(int64_t n, const std::function<void(int64_t)> &fn) {
+    if (n <= 0) return;
+    if (n == 1 || workers_.empty()) { for (int64_t i = 0; i < n; i++) fn(i); return; }
+    std::unique_lock<std::mutex> lk(mu_);
+    while (busy_) done_cv_.wait(lk);           /* one job at a time; concurrent callers queue up */
+    busy_ = true; fn_ = &fn; n_ = n; next_ = 0; left_ = n; gen_++;
+    lk.unlock();
+    work_cv_.notify_all();
+    run_some();
+    lk.lock();
+    while (left_ > 0) done_cv_.wait(lk);
+    busy_ = false; fn_ = nullptr;
+    lk.unlock();
+    done_cv_.notify_all();
+  }
+ private:
+  HostPool() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int n = (int)(hc / 2); if (n > 7) n = 7; if (n < 1) n = 0;
+    for (int i = 0; i < n; i++) { workers_.emplace_back([this] { loop(); }); workers_.back().detach(); }
+  }
+  void run_some() {
+    for (;;) {
+      int64_t i;
+      { std::lock_guard<std::mutex> lk(mu_); if (!fn_ || next_ >= n_) return; i = next_++; }
+      (*fn_)(i);
+      { std::lock_guard<std::mutex> lk(mu_); if (--left_ == 0) done_cv_.notify_all(); }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> lk(mu_); while (gen_ == seen) work_cv_.wait(lk); seen = gen_; }
+      run_some();
+    }
+  }
+  std::mutex mu_; std::condition_variable work_cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int64_t)> *fn_ = nullptr;
+  int64_t n_ = 0, next_ = 0, left_ = 0; uint64_t gen_ = 0; bool busy_ = false;
+};
+
+/* columns [0, cols) of `width` bytes each, pitches in bytes */
+static void host_copy_cols(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t cols) {
+  const size_t total = width * cols;
+  /* waking sleeping pool threads costs up to milliseconds on a virtualised host (measured: a 1024^3
+   * DGEMM call went from 2 ms to 16 ms when its 8 MB operands were split over the pool), so only
+   * copies of at least 16 MB are shared out */
+  int64_t parts = total >= (16u << 20) ? (int64_t)(total / (2u << 20)) : 1;
+  if (parts > 16) parts = 16;
+  if ((size_t)parts > cols) parts = (int64_t)cols;
+  if (parts < 1) parts = 1;
+  HostPool::get().parallel_for(parts, [&](int64_t p) {
+    size_t c0 = cols * (size_t)p / (size_t)parts, c1 = cols * (size_t)(p + 1) / (size_t)parts;
+    if (dpitch == width && spitch == width) { memcpy(dst + c0 * width, src + c0 * width, (c1 - c0) * width); return; }
+    for (size_t c = c0; c < c1; c++) memcpy(dst + c * dpitch, src + c * spitch, width);
+  });
+}
+
+static int ensure_slots(Context *ctx) {
+  if (ctx->in_slot[0]) return 0;
+  for (int i = 0; i < Context::kSlots; i++) {
+    CK(cudaHostAlloc((void **)&ctx->in_slot[i], kSlotBytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&ctx->out_slot[i], kSlotBytes, cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->out_ev[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+static int drain_out(Context *ctx, int k) {
+  Context::PendingOut &po = ctx->out_pending[k];
+  if (!po.active) return 0;
+  CK(cudaEventSynchronize(ctx->out_ev[k]));
+  host_copy_cols(po.host, po.hpitch, ctx->out_slot[k], po.width, po.width, po.cols);
+  po.active = false;
+  return 0;
+}
+static int drain_all_out(Context *ctx) {
+  for (int k = 0; k < Context::kSlots; k++) { int e = drain_out(ctx, k); if (e) return e; }
+  return 0;
+}
+
+/* host (pinned or pageable) -> device, `cols` columns of `width` bytes, enqueued on s */
+static int h2d_any(Context *ctx, cudaStream_t s, PtrKind kind, char *dev, size_t dpitch, const char *host, size_t hpitch,
+                   size_t width, size_t cols) {
+  if (kind != PTR_PAGEABLE || width == 0 || cols == 0) {
+    CK(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, width, cols, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  int err = ensure_slots(ctx);
+  if (err) return err;
+  size_t cpc = kSlotBytes / width;                 /* columns per chunk */
+  if (cpc == 0) {                                   /* a single column larger than a slot: let the driver stage it */
+    CK(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, width, cols, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  for (size_t c0 = 0; c0 < cols; c0 += cpc) {
+    const size_t nc = cols - c0 < cpc ? cols - c0 : cpc;
+    const int k = ctx->in_next; ctx->in_next = (k + 1) % Context::kSlots;
+    if (ctx->in_busy[k]) CK(cudaEventSynchronize(ctx->in_ev[k]));
+    host_copy_cols(ctx->in_slot[k], width, host + c0 * hpitch, hpitch, width, nc);
+    CK(cudaMemcpy2DAsync(dev + c0 * dpitch, dpitch, ctx->in_slot[k], width, width, nc, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->in_ev[k], s));
+    ctx->in_busy[k] = true;
+  }
+  return 0;
+}
+
+/* device -> host; for pageable memory the copy-out of a slot is deferred (drain_out) */
+static int d2h_any(Context *ctx, cudaStream_t s, PtrKind kind, char *host, size_t hpitch, const char *dev, size_t dpitch,
+                   size_t width, size_t cols) {
+  if (kind != PTR_PAGEABLE || width == 0 || cols == 0 || kSlotBytes / width == 0) {
+    CK(cudaMemcpy2DAsync(host, hpitch, dev, dpitch, width, cols, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
+  int err = ensure_slots(ctx);
+  if (err) return err;
+  const size_t cpc = kSlotBytes / width;
+  for (size_t c0 = 0; c0 < cols; c0 += cpc) {
+    const size_t nc = cols - c0 < cpc ? cols - c0 : cpc;
+    const int k = ctx->out_next; ctx->out_next = (k + 1) % Context::kSlots;
+    if ((err = drain_out(ctx, k))) return err;
+    CK(cudaMemcpy2DAsync(ctx->out_slot[k], width, dev + c0 * dpitch, dpitch, width, nc, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->out_ev[k], s));
+    Context::PendingOut &po = ctx->out_pending[k];
+    po.active = true; po.host = host + c0 * hpitch; po.hpitch = hpitch; po.width = width; po.cols = nc;
+  }
+  return 0;
+}
+
 /* Pipelined host path for big problems: C is cut into kPanel x kPanel blocks; row panels of
  * op(A) and column panels of op(B) are uploaded alternately on the H2D stream, every block whose two
  * panels have landed is multiplied on the compute stream, and finished blocks are downloaded on the
@@ -257,8 +411,9 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
   auto upload_a = [&](int64_t i) -> int {
     if (A.kind == PTR_DEVICE) return 0;
     const int64_t i0 = i * kPanel, mb = (p->m - i0 < kPanel) ? p->m - i0 : kPanel;
-    if (!ta) CK(cudaMemcpy2DAsync(A.dev + i0 * ies, A.ld_dev * ies, A.host + i0 * ies, A.ld_user * ies, mb * ies, p->k, cudaMemcpyHostToDevice, si));
-    else     CK(cudaMemcpy2DAsync(A.dev + i0 * A.ld_dev * ies, A.ld_dev * ies, A.host + i0 * A.ld_user * ies, A.ld_user * ies, p->k * ies, mb, cudaMemcpyHostToDevice, si));
+    if (!ta) err = h2d_any(ctx, si, A.kind, A.dev + i0 * ies, A.ld_dev * ies, A.host + i0 * ies, A.ld_user * ies, mb * ies, p->k);
+    else     err = h2d_any(ctx, si, A.kind, A.dev + i0 * A.ld_dev * ies, A.ld_dev * ies, A.host + i0 * A.ld_user * ies, A.ld_user * ies, p->k * ies, mb);
+    if (err) return err;
     if ((err = event_at(ctx, ev++, &ev_a[i]))) return err;
     CK(cudaEventRecord(ev_a[i], si));
     return 0;
@@ -266,8 +421,9 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
   auto upload_b = [&](int64_t j) -> int {
     if (B.kind == PTR_DEVICE) return 0;
     const int64_t j0 = j * kPanel, nb = (p->n - j0 < kPanel) ? p->n - j0 : kPanel;
-    if (!tb) CK(cudaMemcpy2DAsync(B.dev + j0 * B.ld_dev * ies, B.ld_dev * ies, B.host + j0 * B.ld_user * ies, B.ld_user * ies, p->k * ies, nb, cudaMemcpyHostToDevice, si));
-    else     CK(cudaMemcpy2DAsync(B.dev + j0 * ies, B.ld_dev * ies, B.host + j0 * ies, B.ld_user * ies, nb * ies, p->k, cudaMemcpyHostToDevice, si));
+    if (!tb) err = h2d_any(ctx, si, B.kind, B.dev + j0 * B.ld_dev * ies, B.ld_dev * ies, B.host + j0 * B.ld_user * ies, B.ld_user * ies, p->k * ies, nb);
+    else     err = h2d_any(ctx, si, B.kind, B.dev + j0 * ies, B.ld_dev * ies, B.host + j0 * ies, B.ld_user * ies, nb * ies, p->k);
+    if (err) return err;
     if ((err = event_at(ctx, ev++, &ev_b[j]))) return err;
     CK(cudaEventRecord(ev_b[j], si));
     return 0;
@@ -282,7 +438,7 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
     b.c = C.dev + (i0 + j0 * C.ld_dev) * oes;
     if (C.kind != PTR_DEVICE && use_beta) {
       cudaEvent_t e;
-      CK(cudaMemcpy2DAsync((void *)b.c, C.ld_dev * oes, C.host + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, mb * oes, nb, cudaMemcpyHostToDevice, si));
+      if ((err = h2d_any(ctx, si, C.kind, (char *)b.c, C.ld_dev * oes, C.host + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, mb * oes, nb))) return err;
       if ((err = event_at(ctx, ev++, &e))) return err;
       CK(cudaEventRecord(e, si));
       CK(cudaStreamWaitEvent(sc, e, 0));
@@ -295,7 +451,7 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
       if ((err = event_at(ctx, ev++, &e))) return err;
       CK(cudaEventRecord(e, sc));
       CK(cudaStreamWaitEvent(so, e, 0));
-      CK(cudaMemcpy2DAsync((char *)p->c + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, b.c, C.ld_dev * oes, mb * oes, nb, cudaMemcpyDeviceToHost, so));
+      if ((err = d2h_any(ctx, so, C.kind, (char *)p->c + (i0 + j0 * C.ld_user) * oes, C.ld_user * oes, (const char *)b.c, C.ld_dev * oes, mb * oes, nb))) return err;
     }
     return 0;
   };
@@ -309,6 +465,7 @@ static int run_pipelined(Context *ctx, const b200_problem *p, const DeviceGemm &
   }
   CK(cudaStreamSynchronize(si));
   CK(cudaStreamSynchronize(sc));
+  if ((err = drain_all_out(ctx))) return err;
   CK(cudaStreamSynchronize(so));
   return 0;
 }
@@ -411,13 +568,15 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
     if (o.kind == PTR_DEVICE) continue;
     if (i == 2 && !use_beta) continue;
     if (i < 2 && !product) continue;
-    CK(cudaMemcpy2DAsync(o.dev, (size_t)o.ld_dev * o.es, o.host, (size_t)o.ld_user * o.es,
-                         (size_t)o.rows * o.es, (size_t)o.cols, cudaMemcpyHostToDevice, s));
+    if ((err = h2d_any(ctx, s, o.kind, o.dev, (size_t)o.ld_dev * o.es, o.host, (size_t)o.ld_user * o.es,
+                       (size_t)o.rows * o.es, (size_t)o.cols))) return err;
   }
   CK(dispatch(g, s));
-  if (C.kind != PTR_DEVICE)
-    CK(cudaMemcpy2DAsync((void *)p->c, (size_t)C.ld_user * C.es, C.dev, (size_t)C.ld_dev * C.es,
-                         (size_t)C.rows * C.es, (size_t)C.cols, cudaMemcpyDeviceToHost, s));
+  if (C.kind != PTR_DEVICE) {
+    if ((err = d2h_any(ctx, s, C.kind, (char *)p->c, (size_t)C.ld_user * C.es, C.dev, (size_t)C.ld_dev * C.es,
+                       (size_t)C.rows * C.es, (size_t)C.cols))) return err;
+    if ((err = drain_all_out(ctx))) return err;
+  }
   CK(cudaStreamSynchronize(s));
   return 0;
 }

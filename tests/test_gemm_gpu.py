@@ -355,3 +355,15 @@ def test_pipelined_host_path_matches_device_path(ob, oracle, ops):
         col = b[:k, j] if tb else b[j, :k]
         want = alpha * float(np.dot(row, col)) + beta * c0[j, i]
         assert abs(got[j, i] - want) <= 1e-12 * k
+
+
+def test_midsize_pageable_host_operands(ob, oracle):
+    """Between the packed small path (<= 4 MiB) and the panel pipeline: pageable numpy operands go
+    through the threaded pinned-slot staging of runtime.cu (h2d_any / d2h_any), padded lds."""
+    rng = np.random.default_rng(88)
+    m, n, k = 1500, 900, 700
+    for ta, tb in ((0, 0), (1, 0)):
+        a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, ta, tb, m, n, k, pad=(3, 5, 7))
+        got = c0.copy()
+        run_cblas(ob, cpu.D, ob.cblas.ColMajor, ta, tb, m, n, k, 0.7, a, lda, b, ldb, 1.3, got, ldc)
+        check(oracle, cpu.D, ta, tb, m, n, k, 0.7, a, lda, b, ldb, 1.3, c0, ldc, got, "pageable-mid")
