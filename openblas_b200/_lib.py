@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libopenblas_b200.so")
+LIB_PATH = os.environ.get("OPENBLAS_B200_LIB") or os.path.join(_HERE, "lib", "libopenblas_b200.so")   # override: experiments only
 
 
 class LibraryMissing(RuntimeError):

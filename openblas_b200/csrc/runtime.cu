@@ -596,11 +596,90 @@ B200_HIDDEN int b200_run_problem(const b200_problem *p) {
   return run_on_context(lease.c, p);
 }
 
+/* gemm_batch (interface/gemm_batch.c:322-366 hands one queue entry per matrix to the thread pool):
+ * when every operand lives in host memory and the whole batch packs into 64 MB, all A and B
+ * blocks go up in ONE copy, every matrix gets its own kernel launch on one stream, and all C
+ * blocks come back in ONE copy -- one synchronisation per batch instead of one per matrix.
+ * Anything else (device operands, huge matrices) runs matrix by matrix. */
+static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, bool *handled) {
+  *handled = false;
+  struct Item { Operand A, B, C; DeviceGemm g; bool product, use_beta; };
+  std::vector<Item> items((size_t)count);
+  size_t ab_bytes = 0, c_bytes = 0;
+  bool any_beta = false;
+  for (int64_t i = 0; i < count; i++) {
+    Item &it = items[(size_t)i];
+    const b200_problem &q = p[i];
+    DeviceGemm &g = it.g;
+    g.dtype = q.dtype; g.transa = q.transa; g.transb = q.transb; g.m = q.m; g.n = q.n; g.k = q.k;
+    read_scalars(&q, g);
+    it.product = g.k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
+    it.use_beta = !(g.beta_re == 0.0 && g.beta_im == 0.0);
+    any_beta |= it.use_beta;
+    Operand &A = it.A, &B = it.B, &C = it.C;
+    A.es = B.es = b200_in_size(q.dtype); C.es = b200_out_size(q.dtype);
+    A.rows = (q.transa & 1) ? q.k : q.m; A.cols = (q.transa & 1) ? q.m : q.k;
+    B.rows = (q.transb & 1) ? q.n : q.k; B.cols = (q.transb & 1) ? q.k : q.n;
+    C.rows = q.m; C.cols = q.n;
+    A.ld_user = q.lda; B.ld_user = q.ldb; C.ld_user = q.ldc;
+    A.host = (const char *)q.a; B.host = (const char *)q.b; C.host = (const char *)q.c;
+    if ((it.product && (classify(q.a) == PTR_DEVICE || classify(q.b) == PTR_DEVICE)) || classify(q.c) == PTR_DEVICE) return 0;
+    Operand *ops[3] = {&A, &B, &C};
+    for (int o = 0; o < 3; o++) {
+      Operand &x = *ops[o];
+      x.ld_dev = (int64_t)(round_up((size_t)(x.rows > 0 ? x.rows : 1) * x.es, 128) / x.es);
+      if (o < 2) { if (it.product) ab_bytes += round_up(x.bytes_dev(), 256); }
+      else c_bytes += round_up(x.bytes_dev(), 256);
+    }
+  }
+  const size_t total = ab_bytes + c_bytes;
+  if (total > (64u << 20)) return 0;
+  int err = reserve_device(ctx, total);
+  if (err) return err;
+  if ((err = reserve_pinned(ctx, total))) return err;
+  size_t off_ab = 0, off_c = ab_bytes;
+  for (Item &it : items) {
+    if (it.product) {
+      it.A.dev = ctx->dws + off_ab; pack_to(ctx->hws + off_ab, it.A); off_ab += round_up(it.A.bytes_dev(), 256);
+      it.B.dev = ctx->dws + off_ab; pack_to(ctx->hws + off_ab, it.B); off_ab += round_up(it.B.bytes_dev(), 256);
+    } else {
+      it.A.dev = it.B.dev = ctx->dws;
+    }
+    it.C.dev = ctx->dws + off_c;
+    if (it.use_beta) pack_to(ctx->hws + off_c, it.C);
+    off_c += round_up(it.C.bytes_dev(), 256);
+  }
+  cudaStream_t s = ctx->stream;
+  const size_t up = any_beta ? total : ab_bytes;
+  if (up) CK(cudaMemcpyAsync(ctx->dws, ctx->hws, up, cudaMemcpyHostToDevice, s));
+  for (Item &it : items) {
+    DeviceGemm &g = it.g;
+    g.a = it.A.dev; g.b = it.B.dev; g.c = it.C.dev; g.lda = it.A.ld_dev; g.ldb = it.B.ld_dev; g.ldc = it.C.ld_dev;
+    CK(dispatch(g, s));
+  }
+  if (c_bytes) CK(cudaMemcpyAsync(ctx->hws + ab_bytes, ctx->dws + ab_bytes, c_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < items.size(); i++) {
+    Item &it = items[i];
+    if (!it.product && it.g.beta_re == 1.0 && it.g.beta_im == 0.0) continue;     /* C untouched */
+    const Operand &C = it.C;
+    const size_t c_off = (size_t)(C.dev - ctx->dws), row_bytes = (size_t)C.rows * C.es;
+    char *uc = (char *)p[i].c;
+    for (int64_t j = 0; j < C.cols; j++)
+      memcpy(uc + (size_t)j * (size_t)C.ld_user * C.es, ctx->hws + c_off + (size_t)j * (size_t)C.ld_dev * C.es, row_bytes);
+  }
+  *handled = true;
+  return 0;
+}
+
 B200_HIDDEN int b200_run_batch(const b200_problem *p, int64_t count) {
   ContextLease lease;
   int err = acquire(&lease.c);
   if (err) return err;
   t_error[0] = 0;
+  bool handled = false;
+  if ((err = run_batch_packed(lease.c, p, count, &handled))) return err;
+  if (handled) return 0;
   for (int64_t i = 0; i < count; i++) {
     err = run_on_context(lease.c, &p[i]);
     if (err) return err;

@@ -24,7 +24,10 @@
 namespace b200 {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+#ifndef SGEMM_BK
+#define SGEMM_BK 16
+#endif
+constexpr int BM = 128, BN = 128, BK = SGEMM_BK;
 constexpr int STAGES = 3;
 constexpr int THREADS = 256;
 constexpr int LDS = BM + 4;                          /* 132 floats = 528 B (16-byte multiple) */
@@ -103,7 +106,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
     KStager<float, BM, BK, LDS, THREADS> la_k, lb_k;
     if (A_MN) { if (vec_a) la_mn.init(A, g.lda, m0, g.m, tid); } else la_k.init(A, g.lda, m0, g.m, vec_a, tid);
     if (B_MN) { if (vec_b) lb_mn.init(B, g.ldb, n0, g.n, tid); } else lb_k.init(B, g.ldb, n0, g.n, vec_b, tid);
-    float ra[8], rb[8];
+    float ra[BM * BK / THREADS], rb[BN * BK / THREADS];
     /* issue the asynchronous part of k tile `kt_load` (cp.async for mn-contiguous operands, global
      * loads into registers for k-contiguous ones) */
     int req_slot = 0, dep_slot = 0, use_slot = 0;   /* ring positions: next request / deposit / consume */

@@ -210,18 +210,25 @@ def test_gemm3m_and_batch(ob, oracle):
     ob.cblas.zgemm3m(ob.cblas.ColMajor, CB[3], CB[1], m, n, k, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, got, ldc)
     check(oracle, cpu.Z, 3, 1, m, n, k, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, c0, ldc, got, "3m")
 
-    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2)]
+    # (transa, transb, m, n, k, count); the third group reaches the DMMA kernel, the fourth has beta == 0
+    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2), (0, 0, 128, 96, 160, 12), (1, 1, 7, 5, 3, 4)]
+    alphas, betas = [0.7, 1.0, -0.4, 2.0], [1.3, 0.0, 1.0, 0.0]
     probs, ptr_a, ptr_b, ptr_c = [], [], [], []
+    first_of = []
     for (ta, tb, gm, gn, gk, cnt) in groups:
         for _ in range(cnt):
             pa, plda, pb, pldb, pc0, pldc = problem(rng, oracle, cpu.D, ta, tb, gm, gn, gk, pad=(1, 1, 1))
-            probs.append((ta, tb, gm, gn, gk, pa, plda, pb, pldb, pc0, pc0.copy(), pldc))
+            got_c = pc0.copy()
+            if betas[len(first_of)] == 0.0:
+                got_c[:, :gm] = np.nan          # beta == 0 must not read C
+            probs.append((ta, tb, gm, gn, gk, pa, plda, pb, pldb, pc0, got_c, pldc))
+        first_of.append(len(probs))
     I = lambda vals: (C.c_int * len(vals))(*vals)
     ta_arr, tb_arr = I([CB[g[0]] for g in groups]), I([CB[g[1]] for g in groups])
     m_arr, n_arr, k_arr = I([g[2] for g in groups]), I([g[3] for g in groups]), I([g[4] for g in groups])
     first = [sum(g[5] for g in groups[:i]) for i in range(len(groups))]
     lda_arr = I([probs[f][6] for f in first]); ldb_arr = I([probs[f][8] for f in first]); ldc_arr = I([probs[f][11] for f in first])
-    alpha = (C.c_double * 2)(0.7, 1.0); beta = (C.c_double * 2)(1.3, 0.0)
+    alpha = (C.c_double * len(groups))(*alphas); beta = (C.c_double * len(groups))(*betas)
     A = (C.c_void_p * len(probs))(*[p[5].ctypes.data for p in probs])
     B = (C.c_void_p * len(probs))(*[p[7].ctypes.data for p in probs])
     Cc = (C.c_void_p * len(probs))(*[p[10].ctypes.data for p in probs])
