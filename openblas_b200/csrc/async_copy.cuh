@@ -232,6 +232,23 @@ __device__ __forceinline__ void produce_operand(uint32_t s_tile, const void *__r
   const int64_t mn_left = mn_end - mn0, k_left = k_end - k0;
   const bool interior = mn_left >= ROWS && k_left >= BK;
   if (MN_CONTIG) {
+    constexpr bool USE_BULK = ROWS * ES >= 1024;      /* shorter rows: the per-copy cost of the TMA engine would bound the tile */
+    if (interior && !USE_BULK) {
+      constexpr int CPR = ROWS / VE;                  /* 16-byte chunks per k row */
+      static_assert(CPR % 32 == 0, "a k row must be a whole number of warp-wide copies");
+      const char *src = g + (mn0 + lane * VE + k0 * ld) * ES;
+      uint32_t dst = s_tile + (uint32_t)(lane * 16);
+#pragma unroll 8
+      for (int r = 0; r < BK; r++) {
+#pragma unroll
+        for (int j = 0; j < CPR / 32; j++)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 512), "l"(src + j * 512) : "memory");
+        src += ld * ES;
+        dst += LD_MN * ES;
+      }
+      cp_async_mbar_arrive_noinc(bar);
+      return;
+    }
     if (interior) {
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)ROWS * BK * ES); else mbar_arrive(bar);
       __syncwarp();

@@ -408,6 +408,7 @@ using CfgDual   = Cfg<128, 64, 32, 32, 16, 3, 2>;    /* 8 warps, 32x32 warp tile
 using CfgBig    = Cfg<128, 128, 32, 32, 16, 4, 1>;   /* 16 warps, 32x32 warp tiles, 1 CTA/SM                      */
 using CfgWide32 = Cfg<128, 128, 64, 32, 32, 3, 1>;   /* as Wide with k step 32: half as many barriers per flop    */
 using CfgWide32b = Cfg<128, 128, 64, 32, 32, 2, 1>;  /* k step 32, double buffer                                  */
+using CfgMid    = Cfg<64, 64, 32, 16, 32, 5, 1>;     /* producer-warp kernel for grids that leave SMs idle at 128x128 */
 
 }  // namespace
 
@@ -419,6 +420,21 @@ cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   cudaError_t e;
   const char *name;
   if (cfg >= 5 && bulk_eligible<CfgWide32>(g)) {
+    /* Tile choice.  A 128x128 tile costs four 64x64 tiles; the grid runs in waves of one tile per SM.
+     * When the 128x128 tiling leaves SMs idle (few tiles, or a mostly empty last wave) the 64x64
+     * tiling finishes sooner even though it re-reads operands twice as often (33 against 35.5 TFLOP/s
+     * on large grids: penalty 1.08; 1024^3: 26 against 14.6 TFLOP/s, 2048^3: 32.7 against 30.4).  B200_DGEMM_TILE=64|128 forces one. */
+    const char *t = getenv("B200_DGEMM_TILE");
+    const int forced = t ? atoi(t) : 0;
+    const int64_t sms = sm_count();
+    const int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+    const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = 1.08 * (double)((t64 + sms - 1) / sms);
+    const bool small_tile = forced == 64 || (forced != 128 && est64 < est128);
+    if (small_tile) {
+      e = launch_bulk<CfgMid>(g, stream);
+      if (e == cudaSuccess) count_launch("dgemm_dmma_pw_64x64x32_w32x16");
+      return e;
+    }
     e = launch_bulk<CfgWide32>(g, stream);
     if (e == cudaSuccess) count_launch("dgemm_dmma_bulk_128x128x32_w64x32");
     return e;

@@ -603,6 +603,8 @@ B200_HIDDEN int b200_run_problem(const b200_problem *p) {
  * Anything else (device operands, huge matrices) runs matrix by matrix. */
 static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, bool *handled) {
   *handled = false;
+  static const bool enabled = !(getenv("B200_BATCH_PACKED") && atoi(getenv("B200_BATCH_PACKED")) == 0);
+  if (!enabled) return 0;
   struct Item { Operand A, B, C; DeviceGemm g; bool product, use_beta; };
   std::vector<Item> items((size_t)count);
   size_t ab_bytes = 0, c_bytes = 0;

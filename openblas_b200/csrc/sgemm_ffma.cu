@@ -27,13 +27,22 @@ namespace {
 #ifndef SGEMM_BK
 #define SGEMM_BK 16
 #endif
-constexpr int BM = 128, BN = 128, BK = SGEMM_BK;
+constexpr int BK = SGEMM_BK;
 constexpr int STAGES = 3;
-constexpr int THREADS = 256;
-constexpr int LDS = BM + 4;                          /* 132 floats = 528 B (16-byte multiple) */
-constexpr int OPERAND_FLOATS = BK * LDS;
-constexpr int STAGE_FLOATS = 2 * OPERAND_FLOATS;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float);   /* 50688 B */
+/* Square CTA tile TILE x TILE, 8 x 8 outputs per thread.  TILE = 128: 256 threads, 2 CTAs per SM (the
+ * roofline shape).  TILE = 64: 64 threads, up to 8 CTAs per SM -- same warps per SM, four times as
+ * many tiles, for grids that would leave SMs idle at 128 x 128 (1024^3 is only 64 such tiles). */
+template <int TILE>
+struct SC {
+  static constexpr int BM = TILE, BN = TILE;
+  static constexpr int THREADS = TILE * TILE / 64;
+  static constexpr int WARPS_M = TILE / 64;               /* a warp spans 8 (m) x 4 (n) thread positions */
+  static constexpr int MINB = TILE == 128 ? 2 : 8;
+  static constexpr int LDS = TILE + 4;                    /* 132 / 68 floats: 16-byte multiples */
+  static constexpr int OPERAND_FLOATS = BK * LDS;
+  static constexpr int STAGE_FLOATS = 2 * OPERAND_FLOATS;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float);   /* 50688 / 26112 B */
+};
 
 typedef unsigned long long u64;
 
@@ -50,6 +59,7 @@ __device__ __forceinline__ void ffma2(u64 &c, u64 a, u64 b) {
 }
 
 /* Element-wise fallback for an mn-contiguous operand that is not 16-byte aligned. */
+template <int BM, int THREADS, int LDS>
 __device__ __noinline__ void load_mn_unaligned(float *s, const float *__restrict__ g, int64_t ld, int64_t mn0,
                                                int64_t k0, int64_t mn_end, int64_t k_end, int tid) {
   for (int i = 0; i < BM * BK / THREADS; i++) {
@@ -63,17 +73,20 @@ __device__ __noinline__ void load_mn_unaligned(float *s, const float *__restrict
 }
 
 /* PACKED: accumulate with FFMA2 (fma.rn.f32x2) on row pairs; otherwise with scalar FFMA. */
-template <bool A_MN, bool B_MN, int PACKED>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int TILE, bool A_MN, bool B_MN, int PACKED>
+__global__ void __launch_bounds__(SC<TILE>::THREADS, SC<TILE>::MINB)
 sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
+  constexpr int BM = SC<TILE>::BM, BN = SC<TILE>::BN, THREADS = SC<TILE>::THREADS, LDS = SC<TILE>::LDS;
+  constexpr int OPERAND_FLOATS = SC<TILE>::OPERAND_FLOATS, STAGE_FLOATS = SC<TILE>::STAGE_FLOATS;
+  constexpr int HM = BM / 2, HN = BN / 2;                 /* a thread owns rows tm*4..+3 and HM + tm*4..+3; columns likewise */
   extern __shared__ __align__(16) float fsmem[];
   const float *__restrict__ A = (const float *)g.a;
   const float *__restrict__ B = (const float *)g.b;
   float *__restrict__ C = (float *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  /* warp = 8 (m) x 4 (n) threads; warps 2 (m) x 4 (n): thread coordinates in a 16 x 16 grid */
-  const int tm = (warp & 1) * 8 + (lane & 7);
-  const int tn = (warp >> 1) * 4 + (lane >> 3);
+  /* warp = 8 (m) x 4 (n) threads; warps WARPS_M (m) x rest (n): a (TILE/8) x (TILE/8) grid of threads */
+  const int tm = (warp % SC<TILE>::WARPS_M) * 8 + (lane & 7);
+  const int tn = (warp / SC<TILE>::WARPS_M) * 4 + (lane >> 3);
 
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
   const int64_t tiles = tiles_m * tiles_n;
@@ -118,11 +131,11 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       const uint32_t ua = smem_base + (uint32_t)(stage * STAGE_FLOATS * 4), ub = ua + (uint32_t)(OPERAND_FLOATS * 4);
       if (A_MN) {
         if (vec_a) { if (k_left < BK) la_mn.issue_tail(ua, (int)k_left); else la_mn.issue(ua); la_mn.advance(); }
-        else load_mn_unaligned(sa, A, g.lda, m0, kt_load * BK, g.m, g.k, tid);
+        else load_mn_unaligned<BM, THREADS, LDS>(sa, A, g.lda, m0, kt_load * BK, g.m, g.k, tid);
       } else { la_k.fetch(ra, k_left < BK ? (int)k_left : BK); la_k.advance(); }
       if (B_MN) {
         if (vec_b) { if (k_left < BK) lb_mn.issue_tail(ub, (int)k_left); else lb_mn.issue(ub); lb_mn.advance(); }
-        else load_mn_unaligned(sb, B, g.ldb, n0, kt_load * BK, g.n, g.k, tid);
+        else load_mn_unaligned<BM, THREADS, LDS>(sb, B, g.ldb, n0, kt_load * BK, g.n, g.k, tid);
       } else { lb_k.fetch(rb, k_left < BK ? (int)k_left : BK); lb_k.advance(); }
     };
     auto deposit = [&](int64_t kt_load) {   /* register-staged operands: transpose into S[k][mn] */
@@ -150,13 +163,13 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
       use_slot = (use_slot + 1 == STAGES) ? 0 : use_slot + 1;
 #pragma unroll
       for (int k = 0; k < BK; k++) {
-        /* rows tm*4..+3 and 64+tm*4..+3 as two 64-bit pairs each; columns likewise as floats */
+        /* rows tm*4..+3 and HM+tm*4..+3 as two 64-bit pairs each; columns likewise as floats */
         float4 b_lo = *reinterpret_cast<const float4 *>(sb + k * LDS);
-        float4 b_hi = *reinterpret_cast<const float4 *>(sb + k * LDS + 64);
+        float4 b_hi = *reinterpret_cast<const float4 *>(sb + k * LDS + HN);
         float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
         if (PACKED) {
           ulonglong2 a_lo = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS);
-          ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS + 64);
+          ulonglong2 a_hi = *reinterpret_cast<const ulonglong2 *>(sa + k * LDS + HM);
           u64 ap[4] = {a_lo.x, a_lo.y, a_hi.x, a_hi.y};
           if (PACKED == 2) {        /* row pair outer: the 64-bit A operand is the one kept in the reuse cache */
 #pragma unroll
@@ -173,7 +186,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
           }
         } else {
           float4 a_lo = *reinterpret_cast<const float4 *>(sa + k * LDS);
-          float4 a_hi = *reinterpret_cast<const float4 *>(sa + k * LDS + 64);
+          float4 a_hi = *reinterpret_cast<const float4 *>(sa + k * LDS + HM);
           float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
 #pragma unroll
           for (int i = 0; i < 8; i++)
@@ -190,11 +203,11 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
     /* epilogue: column j -> n, row pair p -> m */
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int64_t n = n0 + (j < 4 ? tn * 4 + j : 64 + tn * 4 + (j - 4));
+      const int64_t n = n0 + (j < 4 ? tn * 4 + j : HN + tn * 4 + (j - 4));
       if (n >= g.n) continue;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int64_t m = m0 + h * 64 + tm * 4;
+        const int64_t m = m0 + h * HM + tm * 4;
         if (m >= g.m) continue;
         float v[4];
         if (PACKED) {
@@ -431,20 +444,30 @@ cudaError_t launch_pw_variant(const DeviceGemm &g, cudaStream_t stream, int vec_
   return cudaGetLastError();
 }
 
-template <bool A_MN, bool B_MN, int PACKED>
+template <int TILE, bool A_MN, bool B_MN, int PACKED>
 cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
   static bool configured = false;
-  auto kern = sgemm_ffma_kernel<A_MN, B_MN, PACKED>;
+  using S = SC<TILE>;
+  auto kern = sgemm_ffma_kernel<TILE, A_MN, B_MN, PACKED>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int64_t tiles = ((g.m + BM - 1) / BM) * ((g.n + BN - 1) / BN);
-  int64_t cap = (int64_t)sm_count() * 2;
+  int64_t tiles = ((g.m + S::BM - 1) / S::BM) * ((g.n + S::BN - 1) / S::BN);
+  int64_t cap = (int64_t)sm_count() * S::MINB;
   int grid = (int)(tiles < cap ? tiles : cap);
-  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
+  kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
   return cudaGetLastError();
+}
+
+template <int TILE, int PACKED>
+cudaError_t launch_ops(const DeviceGemm &g, cudaStream_t stream, int vec_a, int vec_b, int vec_c) {
+  const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  if (a_mn && b_mn) return launch_variant<TILE, true, true, PACKED>(g, stream, vec_a, vec_b, vec_c);
+  if (a_mn && !b_mn) return launch_variant<TILE, true, false, PACKED>(g, stream, vec_a, vec_b, vec_c);
+  if (!a_mn && b_mn) return launch_variant<TILE, false, true, PACKED>(g, stream, vec_a, vec_b, vec_c);
+  return launch_variant<TILE, false, false, PACKED>(g, stream, vec_a, vec_b, vec_c);
 }
 
 }  // namespace
@@ -468,22 +491,27 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
     if (e == cudaSuccess) count_launch("sgemm_ffma2_pw_192x128x16");
     return e;
   }
-  if (packed == 2) {
-    if (a_mn && b_mn) e = launch_variant<true, true, 2>(g, stream, vec_a, vec_b, vec_c);
-    else if (a_mn && !b_mn) e = launch_variant<true, false, 2>(g, stream, vec_a, vec_b, vec_c);
-    else if (!a_mn && b_mn) e = launch_variant<false, true, 2>(g, stream, vec_a, vec_b, vec_c);
-    else e = launch_variant<false, false, 2>(g, stream, vec_a, vec_b, vec_c);
-  } else if (packed) {
-    if (a_mn && b_mn) e = launch_variant<true, true, 1>(g, stream, vec_a, vec_b, vec_c);
-    else if (a_mn && !b_mn) e = launch_variant<true, false, 1>(g, stream, vec_a, vec_b, vec_c);
-    else if (!a_mn && b_mn) e = launch_variant<false, true, 1>(g, stream, vec_a, vec_b, vec_c);
-    else e = launch_variant<false, false, 1>(g, stream, vec_a, vec_b, vec_c);
-  } else {
-    if (a_mn && b_mn) e = launch_variant<true, true, 0>(g, stream, vec_a, vec_b, vec_c);
-    else if (a_mn && !b_mn) e = launch_variant<true, false, 0>(g, stream, vec_a, vec_b, vec_c);
-    else if (!a_mn && b_mn) e = launch_variant<false, true, 0>(g, stream, vec_a, vec_b, vec_c);
-    else e = launch_variant<false, false, 0>(g, stream, vec_a, vec_b, vec_c);
+  /* Tile choice: a 128x128 tile costs four 64x64 tiles and CTAs spread evenly over the SMs.  Few 128x128
+   * tiles (or a mostly empty last wave) leave FMA pipes idle, so the 64x64 tiling can win despite twice
+   * the shared-memory traffic per flop.  Measured at 1024^3 (64 against 128): NT 35.8/21.6, NN 25.5/21.0,
+   * TT 26.4/20.3, TN 15.5/18.9 TFLOP/s; on full grids the small tile reaches 85-95 % of the large one
+   * (NT best, register-staged k-contiguous operands worst), hence a penalty per op and never for TN.
+   * B200_SGEMM_TILE=64|128 forces one. */
+  const char *tv = getenv("B200_SGEMM_TILE");
+  const int forced = tv ? atoi(tv) : 0;
+  const int64_t sms = sm_count();
+  const int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+  const double penalty = (a_mn && b_mn) ? 1.15 : (!a_mn && !b_mn) ? 1e9 : 1.3;
+  const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = penalty * (double)((t64 + sms - 1) / sms);   /* per-SM work */
+  const bool small_tile = packed == 1 && (forced == 64 || (forced != 128 && est64 < est128));
+  if (small_tile) {
+    e = launch_ops<64, 1>(g, stream, vec_a, vec_b, vec_c);
+    if (e == cudaSuccess) count_launch("sgemm_ffma2_64x64x16");
+    return e;
   }
+  if (packed == 2) e = launch_ops<128, 2>(g, stream, vec_a, vec_b, vec_c);
+  else if (packed) e = launch_ops<128, 1>(g, stream, vec_a, vec_b, vec_c);
+  else e = launch_ops<128, 0>(g, stream, vec_a, vec_b, vec_c);
   if (e == cudaSuccess) count_launch(packed ? "sgemm_ffma2_128x128x16" : "sgemm_ffma_128x128x16");
   return e;
 }
