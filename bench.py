@@ -34,8 +34,8 @@ FLOP_FACTOR = {"s": 2.0, "d": 2.0, "c": 8.0, "z": 8.0, "sb": 2.0}   # real flops
 # DMMA.8x8x4 issue rate 36.8 TFLOP/s, FFMA 71.1 TFLOP/s (cuBLAS: dgemm 36.0, sgemm-pedantic 66.8).
 PEAK_FALLBACK = {"d": 36.8, "z": 36.8, "s": 71.1, "c": 71.1, "sb": 1590.0}
 # DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from one
-# `ncu --set full` capture of the same shape: profiles/r01_dgemm16384_ncu_full_summary.txt
-NCU_TRAFFIC_BYTES = {("d", 16384, 16384, 16384): 60.937608e9 + 2.152380e9}
+# `ncu --set full` capture of the same shape: profiles/r01_prof_d_16384_final2_summary.txt
+NCU_TRAFFIC_BYTES = {("d", 16384, 16384, 16384): 54.017287e9 + 2.149455e9}
 
 
 def measured_peak(dtype):

@@ -129,6 +129,25 @@ struct TileLoader {
 };
 
 /* ---------------------------------------------------------------------------------------------
+ * Lane -> (m position, n position) inside the 8 x 4 grid of thread tiles a warp of the FFMA kernels
+ * covers.  Each lane reads its A fragment and its B fragment with LDS.128.  Measured with
+ * tools/lds_probe.cu under ncu (profiles/r01_lds_wavefronts.txt): an LDS.128 is served one half-warp
+ * at a time, identical addresses are merged only inside a QUAD of adjacent lanes, and a wavefront
+ * delivers 128 B -- so the cost is (sum over quads of distinct bytes) / 128 B, at least 2.  The
+ * obvious map (m = lane & 7, n = lane >> 3) gives every quad four distinct A chunks: 4 wavefronts
+ * per A load, 2 per B load.  With 2 x 2 quads (below) a quad reads two A chunks and two B chunks,
+ * a half-warp reads 8 contiguous A chunks (128 B, conflict free): 2 wavefronts for either load,
+ * a third less shared-memory traffic for the same instructions. */
+__device__ __forceinline__ void warp_tile_position(int lane, int &pm, int &pn) {
+#ifdef B200_OLD_LANE_MAP
+  pm = lane & 7; pn = lane >> 3;
+#else
+  pm = ((lane >> 2) & 3) * 2 + (lane & 1);
+  pn = (lane >> 4) * 2 + ((lane >> 1) & 1);
+#endif
+}
+
+/* ---------------------------------------------------------------------------------------------
  * KStager: the register-staged, TRANSPOSING path of the FFMA kernels for an operand stored
  * k-contiguous (element (mn,k) at g[k + mn*ld]) whose shared-memory image must be S[k][mn].
  * fetch() issues the thread's 16-byte global loads for the NEXT k tile before the FMA block,

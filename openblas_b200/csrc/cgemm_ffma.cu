@@ -65,8 +65,10 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const float2 *__restrict__ B = (const float2 *)g.b;
   float2 *__restrict__ C = (float2 *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tm = (warp & 1) * 8 + (lane & 7);       /* 0..15: rows tm*2+{0,1}, 32+tm*2+{0,1} */
-  const int tn = (warp >> 1) * 4 + (lane >> 3);     /* 0..15 */
+  int pm, pn;
+  warp_tile_position(lane, pm, pn);
+  const int tm = (warp & 1) * 8 + pm;               /* 0..15: rows tm*2+{0,1}, 32+tm*2+{0,1} */
+  const int tn = (warp >> 1) * 4 + pn;              /* 0..15 */
   const float sgn_a = (g.transa & 2) ? -1.f : 1.f;    /* conj(A) */
   const float sgn_b = (g.transb & 2) ? -1.f : 1.f;    /* conj(B) */
 

@@ -85,8 +85,10 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   float *__restrict__ C = (float *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   /* warp = 8 (m) x 4 (n) threads; warps WARPS_M (m) x rest (n): a (TILE/8) x (TILE/8) grid of threads */
-  const int tm = (warp % SC<TILE>::WARPS_M) * 8 + (lane & 7);
-  const int tn = (warp / SC<TILE>::WARPS_M) * 4 + (lane >> 3);
+  int pm, pn;
+  warp_tile_position(lane, pm, pn);
+  const int tm = (warp % SC<TILE>::WARPS_M) * 8 + pm;
+  const int tn = (warp / SC<TILE>::WARPS_M) * 4 + pn;
 
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
   const int64_t tiles = tiles_m * tiles_n;
@@ -347,7 +349,8 @@ sgemm_ffma_pw_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 
   /* consumers: warp grid 3 (m) x 4 (n), lanes 8 (m) x 4 (n) */
   const int wm = (warp % 3) * 64, wn = (warp / 3) * 32;
-  const int lm = lane & 7, ln = lane >> 3;
+  int lm, ln;
+  warp_tile_position(lane, lm, ln);
   const int a_off = wm + lm * 4, b_off = wn + ln * 4;     /* rows a_off..+3 and a_off+32..+35; cols b_off..+3, b_off+16..+19 */
   const float alpha = (float)g.alpha_re, beta = (float)g.beta_re;
   const bool use_beta = beta != 0.f;

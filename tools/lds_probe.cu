@@ -1,7 +1,7 @@
 // Shared-memory wavefront probe: how many LSU wavefronts one warp-wide LDS.128 / LDS.64 costs for a
 // given lane -> 16-byte (8-byte) chunk pattern.  Run under
 //   ncu --metrics l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum,smsp__inst_executed_op_shared_ld.sum
-// and divide; the program itself prints cycles per load per SM (8 warps issuing back to back).
+// and divide (launch order = the order printed).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -53,6 +53,8 @@ int main() {
       {"v4 (lane>>1)&3", 16, [](int l) { return (l >> 1) & 3; }},
       {"v4 (lane>>4)", 16, [](int l) { return l >> 4; }},
       {"v4 ((lane>>4)<<1)|(lane&1)", 16, [](int l) { return ((l >> 4) << 1) | (l & 1); }},
+      {"v4 ((lane>>2)&3)*2+(lane&1)   (A, 2x2 quads)", 16, [](int l) { return ((l >> 2) & 3) * 2 + (l & 1); }},
+      {"v4 (lane>>4)*2+((lane>>1)&1)  (B, 2x2 quads)", 16, [](int l) { return (l >> 4) * 2 + ((l >> 1) & 1); }},
       {"v2 lane&15", 8, [](int l) { return l & 15; }},
       {"v2 lane>>1", 8, [](int l) { return l >> 1; }},
       {"v2 lane>>3", 8, [](int l) { return l >> 3; }},
@@ -73,8 +75,7 @@ int main() {
       cudaError_t e = cudaDeviceSynchronize();
       cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
       // 8 warps x iters x 16 loads per block, one block per SM
-      printf("%-44s row %3d B: %6.2f cycles per warp-load per SM  (%s)\n", pt.name, row_bytes,
-             (double)h[0] / (8.0 * iters * 16), cudaGetErrorString(e));
+      printf("%-44s row %3d B  (%s)\n", pt.name, row_bytes, cudaGetErrorString(e));   /* launch order = ncu ID order */
     }
   }
   return 0;
