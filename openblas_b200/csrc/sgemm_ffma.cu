@@ -75,7 +75,7 @@ __device__ __noinline__ void load_mn_unaligned(float *s, const float *__restrict
 /* PACKED: accumulate with FFMA2 (fma.rn.f32x2) on row pairs; otherwise with scalar FFMA. */
 template <int TILE, bool A_MN, bool B_MN, int PACKED>
 __global__ void __launch_bounds__(SC<TILE>::THREADS, SC<TILE>::MINB)
-sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
+sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c, int probe) {
   constexpr int BM = SC<TILE>::BM, BN = SC<TILE>::BN, THREADS = SC<TILE>::THREADS, LDS = SC<TILE>::LDS;
   constexpr int OPERAND_FLOATS = SC<TILE>::OPERAND_FLOATS, STAGE_FLOATS = SC<TILE>::STAGE_FLOATS;
   constexpr int HM = BM / 2, HN = BN / 2;                 /* a thread owns rows tm*4..+3 and HM + tm*4..+3; columns likewise */
@@ -96,6 +96,9 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const float alpha = (float)g.alpha_re, beta = (float)g.beta_re;
   const bool use_beta = beta != 0.f;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fsmem);
+  /* (tried: opaque per-lane fragment addresses + inline ld.shared to stop the compiler re-deriving
+   * them from %tid every k tile -- ptxas then rotates the accumulators through 56 MOVs per k tile
+   * and the kernel drops from 56.5 to 52.3 TFLOP/s; left as plain C++ loads) */
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
@@ -153,10 +156,14 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
     }
 
     for (int64_t kt = 0; kt < ktiles; kt++) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
+      /* probe (B200_SGEMM_PROBE, timing experiments only, results are garbage): 1 = no operand
+       * traffic after the first ring fill, 2 = additionally no CTA barrier */
+      if (!(probe == 2 && kt >= STAGES)) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+      }
       const int64_t nk = kt + STAGES - 1;
-      const bool refill = nk < ktiles;
+      const bool refill = nk < ktiles && !(probe && kt >= STAGES);
       if (refill) request(nk);
       cp_async_commit();
 
@@ -460,7 +467,8 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
   int64_t tiles = ((g.m + S::BM - 1) / S::BM) * ((g.n + S::BN - 1) / S::BN);
   int64_t cap = (int64_t)sm_count() * S::MINB;
   int grid = (int)(tiles < cap ? tiles : cap);
-  kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
+  const char *pv = getenv("B200_SGEMM_PROBE");
+  kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c, pv ? atoi(pv) : 0);
   return cudaGetLastError();
 }
 
