@@ -38,6 +38,9 @@ typedef enum CBLAS_ORDER     {CblasRowMajor = 101, CblasColMajor = 102} CBLAS_OR
 typedef enum CBLAS_TRANSPOSE {CblasNoTrans = 111, CblasTrans = 112, CblasConjTrans = 113,
                               CblasConjNoTrans = 114} CBLAS_TRANSPOSE;
 typedef CBLAS_ORDER CBLAS_LAYOUT;
+/* cblas.h:64-66 */
+typedef enum CBLAS_UPLO      {CblasUpper = 121, CblasLower = 122} CBLAS_UPLO;
+typedef enum CBLAS_SIDE      {CblasLeft = 141, CblasRight = 142} CBLAS_SIDE;
 #endif
 
 /* =====================================================================================
@@ -121,6 +124,89 @@ void cblas_sbgemm_batch(enum CBLAS_ORDER Order, const enum CBLAS_TRANSPOSE *Tran
                         const bfloat16 **B_array, const blasint *ldb_array,
                         const float *beta_array, float **C_array, const blasint *ldc_array,
                         blasint group_count, const blasint *group_size);
+
+/* ---- level-3 routines that are "GEMM with a mask" (SURVEY 8(f3)): SYMM/HEMM, SYRK/HERK,
+ *      SYR2K/HER2K.  CBLAS: cblas.h:320-345, 365-378; bodies interface/symm.c:231-442,
+ *      interface/syrk.c:190-402, interface/syr2k.c:190-397.  Fortran: common_interface.h:554-626;
+ *      bodies interface/symm.c:150-229, syrk.c:95-188, syr2k.c:95-188.  Same argument checks,
+ *      xerbla_ names and info numbers as the reference; only the referenced triangle of the
+ *      symmetric / Hermitian operand is read and only the named triangle of C is written. */
+/* SYMM / HEMM (cblas.h:320-327, 365-368) */
+void cblas_ssymm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 float alpha, const float *A, blasint lda, const float *B, blasint ldb, float beta, float *C, blasint ldc);
+void cblas_dsymm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 double alpha, const double *A, blasint lda, const double *B, blasint ldb, double beta, double *C, blasint ldc);
+void cblas_csymm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_zsymm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_chemm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_zhemm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, blasint M, blasint N,
+                 const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+/* SYRK / HERK (cblas.h:329-336, 370-373): HERK takes real alpha and beta */
+void cblas_ssyrk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 float alpha, const float *A, blasint lda, float beta, float *C, blasint ldc);
+void cblas_dsyrk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 double alpha, const double *A, blasint lda, double beta, double *C, blasint ldc);
+void cblas_csyrk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 const void *alpha, const void *A, blasint lda, const void *beta, void *C, blasint ldc);
+void cblas_zsyrk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 const void *alpha, const void *A, blasint lda, const void *beta, void *C, blasint ldc);
+void cblas_cherk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 float alpha, const void *A, blasint lda, float beta, void *C, blasint ldc);
+void cblas_zherk(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                 double alpha, const void *A, blasint lda, double beta, void *C, blasint ldc);
+/* SYR2K / HER2K (cblas.h:338-345, 375-378): HER2K takes a complex alpha and a real beta */
+void cblas_ssyr2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  float alpha, const float *A, blasint lda, const float *B, blasint ldb, float beta, float *C, blasint ldc);
+void cblas_dsyr2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  double alpha, const double *A, blasint lda, const double *B, blasint ldb, double beta, double *C, blasint ldc);
+void cblas_csyr2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_zsyr2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, const void *beta, void *C, blasint ldc);
+void cblas_cher2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, float beta, void *C, blasint ldc);
+void cblas_zher2k(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE Trans, blasint N, blasint K,
+                  const void *alpha, const void *A, blasint lda, const void *B, blasint ldb, double beta, void *C, blasint ldc);
+/* Fortran ABI (common_interface.h:554-626): every argument by reference, complex scalars as pointers to (re, im) */
+void ssymm_(char *SIDE, char *UPLO, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+            float *beta, float *c, blasint *ldC);
+void dsymm_(char *SIDE, char *UPLO, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+            double *beta, double *c, blasint *ldC);
+void csymm_(char *SIDE, char *UPLO, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+            float *beta, float *c, blasint *ldC);
+void zsymm_(char *SIDE, char *UPLO, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+            double *beta, double *c, blasint *ldC);
+void chemm_(char *SIDE, char *UPLO, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+            float *beta, float *c, blasint *ldC);
+void zhemm_(char *SIDE, char *UPLO, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+            double *beta, double *c, blasint *ldC);
+void ssyrk_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *beta, float *c,
+            blasint *ldC);
+void dsyrk_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *beta, double *c,
+            blasint *ldC);
+void csyrk_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *beta, float *c,
+            blasint *ldC);
+void zsyrk_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *beta, double *c,
+            blasint *ldC);
+void cherk_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *beta, float *c,
+            blasint *ldC);
+void zherk_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *beta, double *c,
+            blasint *ldC);
+void ssyr2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+             float *beta, float *c, blasint *ldC);
+void dsyr2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+             double *beta, double *c, blasint *ldC);
+void csyr2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+             float *beta, float *c, blasint *ldC);
+void zsyr2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+             double *beta, double *c, blasint *ldC);
+void cher2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, float *a, blasint *ldA, float *b, blasint *ldB,
+             float *beta, float *c, blasint *ldC);
+void zher2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
+             double *beta, double *c, blasint *ldC);
 
 /* ---- bf16 conversion helpers callers of sbgemm need (cblas.h:433-440;
  *      interface/tobf16.c, interface/bf16to.c; rounding rule kernel/x86_64/tobf16.c:46-96) */

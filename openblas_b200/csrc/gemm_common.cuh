@@ -61,6 +61,12 @@ cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t stream);
 cudaError_t launch_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
                            int64_t inc_out, cudaStream_t stream);
 
+/* level3_aux.cu: helpers of the symmetric level-3 family */
+cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out,
+                                    int64_t ldo, cudaStream_t stream);
+cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const void *t, int64_t ldt, double beta_re,
+                             double beta_im, void *c, int64_t ldc, cudaStream_t stream);
+
 int sm_count();
 
 }  // namespace b200

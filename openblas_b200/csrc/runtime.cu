@@ -581,6 +581,8 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
   return 0;
 }
 
+#include "runtime_level3.inl"
+
 }  // namespace b200
 
 /* ------------------------------------------------------------------------ C ABI ---- */
@@ -594,6 +596,19 @@ B200_HIDDEN int b200_run_problem(const b200_problem *p) {
   if (err) return err;
   t_error[0] = 0;
   return run_on_context(lease.c, p);
+}
+
+B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
+  {  /* nothing to do (alpha == 0 or k == 0 with beta == 1): return before CUDA is touched */
+    const bool symm = p->routine == B200_SYMM || p->routine == B200_HEMM;
+    const bool product = !(p->alpha[0] == 0.0 && p->alpha[1] == 0.0) && (symm || p->k > 0);
+    if (!product && p->beta[0] == 1.0 && p->beta[1] == 0.0) return 0;
+  }
+  ContextLease lease;
+  int err = acquire(&lease.c);
+  if (err) return err;
+  t_error[0] = 0;
+  return run_level3_on_context(lease.c, p);
 }
 
 /* gemm_batch (interface/gemm_batch.c:322-366 hands one queue entry per matrix to the thread pool):

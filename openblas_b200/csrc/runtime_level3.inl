@@ -1,0 +1,190 @@
+/*
+ * runtime_level3.inl -- device side of SYMM/HEMM, SYRK/HERK, SYR2K/HER2K (included by runtime.cu
+ * inside namespace b200).  These routines share the GEMM kernels in the reference too
+ * (driver/level3/symm_k.c runs the GEMM loop nest over a symmetric packer; level3_syrk.c and
+ * level3_syr2k.c run it over the triangle with syrk_kernel.c masking the diagonal blocks); here:
+ *
+ *   SYMM / HEMM   the referenced triangle is expanded ONCE into a full matrix in workspace
+ *                 (O(ka^2) bytes of HBM traffic against O(ka^2 * n) flops) and the product is one
+ *                 GEMM at the GEMM kernels' speed;
+ *   SYRK family   C is cut into block columns of width NB.  The rectangle strictly inside the
+ *                 triangle is a plain GEMM straight into C; the NB x NB diagonal block is computed
+ *                 in full into a scratch tile and merged under the triangle mask (tri_merge), which
+ *                 also applies beta and, for HERK/HER2K, zeroes the diagonal's imaginary part.
+ *                 Wasted flops: NB / n of the total.
+ *
+ * Host operands are staged whole (A, B, and the full m x n rectangle of C -- the part of C
+ * outside the triangle travels up and comes back bit-identical; rows beyond m never move).
+ */
+
+static cudaError_t gemm_on_device(int dtype, int ta, int tb, int64_t m, int64_t n, int64_t k, double ar, double ai,
+                                  const void *a, int64_t lda, const void *b, int64_t ldb, double br, double bi, void *c,
+                                  int64_t ldc, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  DeviceGemm g;
+  g.dtype = dtype; g.transa = ta; g.transb = tb; g.m = m; g.n = n; g.k = k;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a = a; g.b = b; g.c = c;
+  g.alpha_re = ar; g.alpha_im = ai; g.beta_re = br; g.beta_im = bi;
+  return dispatch(g, s);
+}
+
+static int64_t rankk_block(int64_t n) { return n >= 4096 ? 512 : n >= 1024 ? 256 : 128; }
+
+/* everything on the device, pointers are device pointers; scratch holds the expanded operand
+ * (SYMM/HEMM) or one NB x NB tile (the others) */
+static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda, const char *b, int64_t ldb, char *c,
+                            int64_t ldc, char *scratch, cudaStream_t s) {
+  const size_t es = b200_in_size(p->dtype);
+  const double ar = p->alpha[0], ai = p->alpha[1], br = p->beta[0], bi = p->beta[1];
+  const bool alpha_zero = ar == 0.0 && ai == 0.0;
+
+  if (p->routine == B200_SYMM || p->routine == B200_HEMM) {
+    if (alpha_zero) {                  /* C := beta * C (beta == 0: exact zeros, C not read) */
+      CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, 0, 0.0, 0.0, c, ldc, c, ldc, br, bi, c, ldc, s));
+      return 0;
+    }
+    const int64_t ka = p->side ? p->n : p->m;
+    const int64_t ldf = (int64_t)(round_up((size_t)ka * es, 128) / es);
+    CK(launch_expand_symmetric(p->dtype, p->uplo, p->routine == B200_HEMM, ka, a, lda, scratch, ldf, s));
+    if (!p->side) CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->m, ar, ai, scratch, ldf, b, ldb, br, bi, c, ldc, s));
+    else CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->n, ar, ai, b, ldb, scratch, ldf, br, bi, c, ldc, s));
+    return 0;
+  }
+
+  const bool herm = p->routine == B200_HERK || p->routine == B200_HER2K;
+  const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
+  const int64_t n = p->n, k = p->k;
+  const bool product = k > 0 && !alpha_zero;
+  if (!product) {                      /* only the triangle is scaled; beta == 1 leaves C alone */
+    if (br == 1.0 && bi == 0.0) return 0;
+    CK(launch_tri_merge(p->dtype, p->uplo, herm, n, nullptr, 0, br, bi, c, ldc, s));
+    return 0;
+  }
+  /* first factor op(X) (rows of C), second factor op(Y)^T or op(Y)^H (columns of C):
+   *   trans == 0: X is n x k, rows i0.. start at X + i0;        first N, second T (or C)
+   *   trans == 1: X is k x n, rows i0.. start at X + i0 * ldx;  first T (or C), second N */
+  const int op_first = p->trans ? (herm ? B200_C_ : B200_T) : B200_N;
+  const int op_second = p->trans ? B200_N : (herm ? B200_C_ : B200_T);
+  auto at = [&](const char *x, int64_t ldx, int64_t i0) { return x + (p->trans ? (size_t)i0 * (size_t)ldx : (size_t)i0) * es; };
+  const double ai2 = herm ? -ai : ai;  /* HER2K: the second product carries conj(alpha) */
+  const int64_t nb = rankk_block(n);
+  const int64_t ldt = (int64_t)(round_up((size_t)nb * es, 128) / es);
+  for (int64_t j0 = 0; j0 < n; j0 += nb) {
+    const int64_t jb = n - j0 < nb ? n - j0 : nb;
+    /* rectangle inside the triangle: rows below the diagonal block (lower) or above it (upper) */
+    const int64_t i0 = p->uplo ? j0 + jb : 0, mr = p->uplo ? n - j0 - jb : j0;
+    char *c_rect = c + ((size_t)i0 + (size_t)j0 * (size_t)ldc) * es;
+    if (mr > 0) {
+      CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai, at(a, lda, i0), lda, at(two ? b : a, two ? ldb : lda, j0),
+                        two ? ldb : lda, br, bi, c_rect, ldc, s));
+      if (two) CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai2, at(b, ldb, i0), ldb, at(a, lda, j0), lda, 1.0, 0.0,
+                                 c_rect, ldc, s));
+    }
+    /* diagonal block through the scratch tile */
+    CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai, at(a, lda, j0), lda, at(two ? b : a, two ? ldb : lda, j0),
+                      two ? ldb : lda, 0.0, 0.0, scratch, ldt, s));
+    if (two) CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai2, at(b, ldb, j0), ldb, at(a, lda, j0), lda, 1.0, 0.0,
+                               scratch, ldt, s));
+    CK(launch_tri_merge(p->dtype, p->uplo, herm, jb, scratch, ldt, br, bi, c + ((size_t)j0 + (size_t)j0 * (size_t)ldc) * es, ldc, s));
+  }
+  return 0;
+}
+
+static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
+  const size_t es = b200_in_size(p->dtype);
+  const bool symm = p->routine == B200_SYMM || p->routine == B200_HEMM;
+  const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
+  const bool alpha_zero = p->alpha[0] == 0.0 && p->alpha[1] == 0.0;
+  const bool beta_one = p->beta[0] == 1.0 && p->beta[1] == 0.0, beta_zero = p->beta[0] == 0.0 && p->beta[1] == 0.0;
+  const bool product = !alpha_zero && (symm || p->k > 0);
+  if (!product && beta_one) return 0;
+
+  Operand A, B, C;
+  A.es = B.es = C.es = es;
+  if (symm) {
+    const int64_t ka = p->side ? p->n : p->m;
+    A.rows = A.cols = ka; B.rows = p->m; B.cols = p->n;
+  } else {
+    A.rows = p->trans ? p->k : p->n; A.cols = p->trans ? p->n : p->k;
+    B.rows = A.rows; B.cols = A.cols;
+  }
+  C.rows = p->m; C.cols = p->n;
+  A.ld_user = p->lda; B.ld_user = p->ldb; C.ld_user = p->ldc;
+  const bool use_b = product && (symm || two);
+  A.kind = product ? classify(p->a) : PTR_DEVICE;
+  B.kind = use_b ? classify(p->b) : PTR_DEVICE;
+  C.kind = classify(p->c);
+  if ((product && A.kind == PTR_DEVICE) || (use_b && B.kind == PTR_DEVICE) || C.kind == PTR_DEVICE) CK(cudaDeviceSynchronize());
+
+  Operand *ops[3] = {&A, &B, &C};
+  const void *user[3] = {p->a, p->b, p->c};
+  const bool needed[3] = {product, use_b, true};
+  size_t need = 0;
+  for (int i = 0; i < 3; i++) {
+    Operand &o = *ops[i];
+    if (!needed[i]) continue;
+    if (o.kind == PTR_DEVICE) { o.dev = (char *)user[i]; o.ld_dev = o.ld_user; continue; }
+    o.host = (const char *)user[i];
+    o.ld_dev = (int64_t)(round_up((size_t)(o.rows > 0 ? o.rows : 1) * o.es, 128) / o.es);
+    need += round_up(o.bytes_dev(), 256);
+  }
+  size_t scratch_bytes = 0;
+  if (product) {
+    const int64_t edge = symm ? A.rows : rankk_block(p->n);
+    scratch_bytes = round_up(round_up((size_t)edge * es, 128) * (size_t)edge, 256);
+  }
+  int err = reserve_device(ctx, need + scratch_bytes);
+  if (err) return err;
+  size_t off = 0;
+  for (int i = 0; i < 3; i++) {
+    Operand &o = *ops[i];
+    if (!needed[i] || o.kind == PTR_DEVICE) continue;
+    o.dev = ctx->dws + off;
+    off += round_up(o.bytes_dev(), 256);
+  }
+  char *scratch = ctx->dws + need;
+
+  cudaStream_t s = ctx->stream;
+  /* C goes up unless it is written in full without being read (SYMM/HEMM with beta == 0): the
+   * triangular routines bring the whole rectangle back, so the untouched triangle must be there */
+  const bool c_up = !(symm && beta_zero);
+  const bool small = need > 0 && need <= kSmallBytes;
+  if (small) {
+    if ((err = reserve_pinned(ctx, need))) return err;
+    size_t up_begin = (size_t)-1, up_end = 0;
+    for (int i = 0; i < 3; i++) {
+      Operand &o = *ops[i];
+      if (!needed[i] || o.kind == PTR_DEVICE || (i == 2 && !c_up)) continue;
+      const size_t o_off = (size_t)(o.dev - ctx->dws);
+      pack_to(ctx->hws + o_off, o);
+      if (o_off < up_begin) up_begin = o_off;
+      if (o_off + o.bytes_dev() > up_end) up_end = o_off + o.bytes_dev();
+    }
+    if (up_end > up_begin) CK(cudaMemcpyAsync(ctx->dws + up_begin, ctx->hws + up_begin, up_end - up_begin, cudaMemcpyHostToDevice, s));
+  } else {
+    for (int i = 0; i < 3; i++) {
+      Operand &o = *ops[i];
+      if (!needed[i] || o.kind == PTR_DEVICE || (i == 2 && !c_up)) continue;
+      if ((err = h2d_any(ctx, s, o.kind, o.dev, (size_t)o.ld_dev * o.es, o.host, (size_t)o.ld_user * o.es, (size_t)o.rows * o.es,
+                         (size_t)o.cols))) return err;
+    }
+  }
+  if ((err = level3_on_device(p, A.dev, A.ld_dev, B.dev, B.ld_dev, C.dev, C.ld_dev, scratch, s))) return err;
+  if (C.kind != PTR_DEVICE) {
+    if (small) {
+      const size_t c_off = (size_t)(C.dev - ctx->dws);
+      CK(cudaMemcpyAsync(ctx->hws + c_off, C.dev, C.bytes_dev(), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      const size_t row_bytes = (size_t)C.rows * C.es;
+      char *uc = (char *)p->c;
+      for (int64_t j = 0; j < C.cols; j++)
+        memcpy(uc + (size_t)j * (size_t)C.ld_user * C.es, ctx->hws + c_off + (size_t)j * (size_t)C.ld_dev * C.es, row_bytes);
+      return 0;
+    }
+    if ((err = d2h_any(ctx, s, C.kind, (char *)p->c, (size_t)C.ld_user * C.es, C.dev, (size_t)C.ld_dev * C.es, (size_t)C.rows * C.es,
+                       (size_t)C.cols))) return err;
+    if ((err = drain_all_out(ctx))) return err;
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}

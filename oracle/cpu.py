@@ -39,8 +39,8 @@ def scalar_bytes(dtype, value):
 
 def build_oracle():
     so = os.path.join(HERE, "_build", "liboracle.so")
-    src = os.path.join(HERE, "gemm_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("gemm_oracle.c", "level3_oracle.c")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -68,6 +68,16 @@ class Oracle:
         L.oracle_bf16_to_f32.restype = C.c_float
         L.oracle_bf16_to_f32.argtypes = [C.c_uint16]
         L.oracle_tobf16.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.oracle_symm.restype = C.c_int
+        L.oracle_symm.argtypes = [C.c_int] * 4 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                                  C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_rankk.restype = C.c_int
+        L.oracle_rankk.argtypes = [C.c_int] * 5 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                                   C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_check_symm.restype = C.c_int
+        L.oracle_check_symm.argtypes = [C.c_int, C.c_int] + [C.c_long] * 5 + [C.c_int]
+        L.oracle_check_rankk.restype = C.c_int
+        L.oracle_check_rankk.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_long] * 5 + [C.c_int]
         L.oracle_bf16to.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
 
     def gemm(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, q=0, unroll_m=0, small=False):
@@ -94,6 +104,28 @@ class Oracle:
 
     def check_args(self, ta, tb, m, n, k, lda, ldb, ldc, ok):
         return self.lib.oracle_check_args(ta, tb, m, n, k, lda, ldb, ldc, ok)
+
+    def symm(self, dtype, herm, side, uplo, m, n, alpha, a, lda, b, ldb, beta, c, ldc):
+        """SYMM (herm=0) / HEMM (herm=1) in place on c; returns the m x n gauge (column-major, as (n, m) array)."""
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        g = np.zeros((max(n, 1), max(m, 1)), dtype=np.float64)
+        assert self.lib.oracle_symm(dtype, herm, side, uplo, m, n, _ptr(al), _ptr(a), lda, _ptr(b), ldb, _ptr(be), _ptr(c),
+                                    ldc, _ptr(g)) == 0
+        return g
+
+    def rankk(self, dtype, herm, two, uplo, trans, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """SYRK/HERK (two=0) or SYR2K/HER2K (two=1) in place on c; returns the n x n gauge (0 outside the triangle)."""
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        g = np.zeros((max(n, 1), max(n, 1)), dtype=np.float64)
+        assert self.lib.oracle_rankk(dtype, herm, two, uplo, trans, n, k, _ptr(al), _ptr(a), lda, _ptr(b if two else a),
+                                     ldb if two else lda, _ptr(be), _ptr(c), ldc, _ptr(g)) == 0
+        return g
+
+    def check_symm(self, side, uplo, m, n, lda, ldb, ldc, ok):
+        return self.lib.oracle_check_symm(side, uplo, m, n, lda, ldb, ldc, ok)
+
+    def check_rankk(self, two, uplo, trans, n, k, lda, ldb, ldc, ok):
+        return self.lib.oracle_check_rankk(two, uplo, trans, n, k, lda, ldb, ldc, ok)
 
     def tobf16(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -136,6 +168,37 @@ def ref_path(target=None):
 
 def have_reference(target=None):
     return os.path.exists(ref_path(target))
+
+
+def _real_scalar(dtype, value):
+    return np.array([float(np.real(value))], dtype=np.float32 if dtype in (S, CX) else np.float64)
+
+
+def call_symm(lib, dtype, herm, side, uplo, m, n, alpha, a, lda, b, ldb, beta, c, ldc):
+    """?symm_ / ?hemm_ of ANY library exporting the Fortran ABI (common_interface.h:554-605): the
+    reference (oracle/_ref) in the pin tests, the library under test in the GPU tests."""
+    fn = getattr(lib, DTYPE_NAMES[dtype] + ("hemm_" if herm else "symm_"))
+    al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+    i = lambda v: C.byref(C.c_int(int(v)))
+    fn(C.c_char_p(b"LR"[side:side + 1]), C.c_char_p(b"UL"[uplo:uplo + 1]), i(m), i(n), _ptr(al), _ptr(a), i(lda), _ptr(b),
+       i(ldb), _ptr(be), _ptr(c), i(ldc))
+    return c
+
+
+def call_rankk(lib, dtype, herm, two, uplo, trans, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+    """?syrk_ / ?herk_ / ?syr2k_ / ?her2k_ (common_interface.h:574-626).  HERK takes real alpha and
+    beta, HER2K complex alpha and real beta."""
+    name = DTYPE_NAMES[dtype] + {(0, 0): "syrk_", (1, 0): "herk_", (0, 1): "syr2k_", (1, 1): "her2k_"}[(herm, two)]
+    fn = getattr(lib, name)
+    al = _real_scalar(dtype, alpha) if (herm and not two) else scalar_bytes(dtype, alpha)
+    be = _real_scalar(dtype, beta) if herm else scalar_bytes(dtype, beta)
+    i = lambda v: C.byref(C.c_int(int(v)))
+    tch = (b"NC" if herm else b"NT")[trans:trans + 1]
+    args = [C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(tch), i(n), i(k), _ptr(al), _ptr(a), i(lda)]
+    if two:
+        args += [_ptr(b), i(ldb)]
+    fn(*(args + [_ptr(be), _ptr(c), i(ldc)]))
+    return c
 
 
 class Reference:

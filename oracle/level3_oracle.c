@@ -1,0 +1,184 @@
+/*
+ * level3_oracle.c -- TEST INFRASTRUCTURE.  CPU restatement of the symmetric level-3 family
+ * (SYMM/HEMM, SYRK/HERK, SYR2K/HER2K) used to check the CUDA path; never linked into the product.
+ *
+ * It follows the SEMANTICS the reference implements -- the netlib definitions the reference
+ * ships under reference/ and its ctest drivers check against:
+ *   reference/dsymmf.f:206-296, zhemmf.f:211-304   which triangle of A is read, the Hermitian
+ *                                                  diagonal taken as real, beta == 0 never reads C
+ *   reference/dsyrkf.f:170-262, zherkf.f:180-330   only the named triangle of C is written;
+ *                                                  alpha == 0 or k == 0 scales that triangle only,
+ *                                                  beta == 1 then leaves C untouched; HERK/HER2K
+ *                                                  force the diagonal's imaginary part to zero
+ *   reference/dsyr2kf.f:176-326, zher2kf.f:187-369 the two products, conj(alpha) on the second
+ * The SUMMATION ORDER is its own (one dot product per element of C, in the working precision of
+ * the type), so it is compared with the reference's optimised drivers (driver/level3/symm_k.c,
+ * level3_syrk.c, level3_syr2k.c, compiled into oracle/_ref) through the componentwise bound
+ * c*k*eps*gauge, not bit for bit: PARITY PINNED BY BOUND against oracle/_ref in
+ * tests/test_oracle_pin.py, not bit-exact (the GEMM oracle in gemm_oracle.c is the bit-exact one).
+ *
+ * `gauge` (optional, m x n doubles, leading dimension m): |alpha| * sum |x||y| + |beta| * |c0|
+ * per element with |z| = |re| + |im| (ABS1 of ctest/c_zblat3.f:2478); 0 for untouched elements.
+ */
+#include <math.h>
+#include <stddef.h>
+#include <string.h>
+
+enum { OR_S = 0, OR_D = 1, OR_C = 2, OR_Z = 3 };
+
+#define GEN(T, SFX)                                                                                         \
+  typedef struct { T re, im; } cx_##SFX;                                                                    \
+  static cx_##SFX ld_##SFX(const T *p, long idx, int cplx) {                                                \
+    cx_##SFX v;                                                                                             \
+    if (cplx) { v.re = p[2 * idx]; v.im = p[2 * idx + 1]; } else { v.re = p[idx]; v.im = 0; }               \
+    return v;                                                                                               \
+  }                                                                                                         \
+  static void st_##SFX(T *p, long idx, int cplx, cx_##SFX v) {                                              \
+    if (cplx) { p[2 * idx] = v.re; p[2 * idx + 1] = v.im; } else p[idx] = v.re;                             \
+  }                                                                                                         \
+  static cx_##SFX mul_##SFX(cx_##SFX x, cx_##SFX y) {                                                       \
+    cx_##SFX r; r.re = x.re * y.re - x.im * y.im; r.im = x.re * y.im + x.im * y.re; return r;               \
+  }                                                                                                         \
+  static cx_##SFX add_##SFX(cx_##SFX x, cx_##SFX y) { cx_##SFX r; r.re = x.re + y.re; r.im = x.im + y.im; return r; } \
+  static cx_##SFX cj_##SFX(cx_##SFX x, int on) { if (on) x.im = -x.im; return x; }                          \
+  static double a1_##SFX(cx_##SFX x) { return fabs((double)x.re) + fabs((double)x.im); }                    \
+  /* element (i, l) of the symmetric / Hermitian matrix stored in one triangle */                          \
+  static cx_##SFX sym_##SFX(const T *a, long lda, int uplo, int herm, int cplx, long i, long l) {           \
+    int stored = uplo ? (i >= l) : (i <= l);                                                                \
+    cx_##SFX v = stored ? ld_##SFX(a, i + l * lda, cplx) : cj_##SFX(ld_##SFX(a, l + i * lda, cplx), herm);  \
+    if (herm && i == l) v.im = 0;                                                                           \
+    return v;                                                                                               \
+  }                                                                                                         \
+  static void symm_##SFX(int cplx, int herm, int side, int uplo, long m, long n, const T *alpha, const T *a, \
+                         long lda, const T *b, long ldb, const T *beta, T *c, long ldc, double *gauge) {     \
+    cx_##SFX al = ld_##SFX(alpha, 0, cplx), be = ld_##SFX(beta, 0, cplx);                                   \
+    int beta_zero = be.re == 0 && be.im == 0;                                                               \
+    long ka = side ? n : m;                                                                                 \
+    for (long j = 0; j < n; j++)                                                                            \
+      for (long i = 0; i < m; i++) {                                                                        \
+        cx_##SFX acc = {0, 0};                                                                              \
+        double g = 0;                                                                                       \
+        for (long l = 0; l < ka; l++) {                                                                     \
+          cx_##SFX x = side ? ld_##SFX(b, i + l * ldb, cplx) : sym_##SFX(a, lda, uplo, herm, cplx, i, l);   \
+          cx_##SFX y = side ? sym_##SFX(a, lda, uplo, herm, cplx, l, j) : ld_##SFX(b, l + j * ldb, cplx);   \
+          acc = add_##SFX(acc, mul_##SFX(x, y));                                                            \
+          g += a1_##SFX(x) * a1_##SFX(y);                                                                   \
+        }                                                                                                   \
+        cx_##SFX r = mul_##SFX(al, acc);                                                                    \
+        g *= a1_##SFX(al);                                                                                  \
+        if (!beta_zero) {                                                                                   \
+          cx_##SFX c0 = ld_##SFX(c, i + j * ldc, cplx);                                                     \
+          r = add_##SFX(r, mul_##SFX(be, c0));                                                              \
+          g += a1_##SFX(be) * a1_##SFX(c0);                                                                 \
+        }                                                                                                   \
+        st_##SFX(c, i + j * ldc, cplx, r);                                                                  \
+        if (gauge) gauge[i + j * m] = g;                                                                    \
+      }                                                                                                     \
+  }                                                                                                         \
+  static void rankk_##SFX(int cplx, int herm, int two, int uplo, int trans, long n, long k, const T *alpha,   \
+                          const T *a, long lda, const T *b, long ldb, const T *beta, T *c, long ldc,          \
+                          double *gauge) {                                                                   \
+    cx_##SFX al = ld_##SFX(alpha, 0, cplx), be = ld_##SFX(beta, 0, cplx);                                   \
+    if (herm && !two) al.im = 0;                                                                            \
+    if (herm) be.im = 0;                                                                                    \
+    int product = k > 0 && !(al.re == 0 && al.im == 0);                                                     \
+    int beta_zero = be.re == 0 && be.im == 0, beta_one = be.re == 1 && be.im == 0;                          \
+    if (gauge) for (long x = 0; x < n * n; x++) gauge[x] = 0;                                               \
+    if (!product && beta_one) return;                                                                       \
+    for (long j = 0; j < n; j++)                                                                            \
+      for (long i = uplo ? j : 0; i < (uplo ? n : j + 1); i++) {                                            \
+        cx_##SFX acc1 = {0, 0}, acc2 = {0, 0};                                                              \
+        double g = 0;                                                                                       \
+        if (product)                                                                                        \
+          for (long l = 0; l < k; l++) {                                                                    \
+            /* first factor: row i of op(A); second: row j of op(B) (B == A for rank-k), conjugated for the Hermitian ones */ \
+            cx_##SFX x = trans ? cj_##SFX(ld_##SFX(a, l + i * lda, cplx), herm) : ld_##SFX(a, i + l * lda, cplx);  \
+            cx_##SFX y = trans ? ld_##SFX(two ? b : a, l + j * (two ? ldb : lda), cplx)                     \
+                               : cj_##SFX(ld_##SFX(two ? b : a, j + l * (two ? ldb : lda), cplx), herm);    \
+            acc1 = add_##SFX(acc1, mul_##SFX(x, y));                                                        \
+            g += a1_##SFX(x) * a1_##SFX(y);                                                                 \
+            if (two) {                                                                                      \
+              cx_##SFX u = trans ? cj_##SFX(ld_##SFX(b, l + i * ldb, cplx), herm) : ld_##SFX(b, i + l * ldb, cplx); \
+              cx_##SFX v = trans ? ld_##SFX(a, l + j * lda, cplx) : cj_##SFX(ld_##SFX(a, j + l * lda, cplx), herm); \
+              acc2 = add_##SFX(acc2, mul_##SFX(u, v));                                                      \
+              g += a1_##SFX(u) * a1_##SFX(v);                                                               \
+            }                                                                                               \
+          }                                                                                                 \
+        cx_##SFX r = mul_##SFX(al, acc1);                                                                   \
+        if (two) r = add_##SFX(r, mul_##SFX(cj_##SFX(al, herm), acc2));                                     \
+        g *= a1_##SFX(al);                                                                                  \
+        if (!beta_zero) {                                                                                   \
+          cx_##SFX c0 = ld_##SFX(c, i + j * ldc, cplx);                                                     \
+          if (herm && i == j) c0.im = 0;                                                                    \
+          r = add_##SFX(r, mul_##SFX(be, c0));                                                              \
+          g += a1_##SFX(be) * a1_##SFX(c0);                                                                 \
+        }                                                                                                   \
+        if (herm && i == j) r.im = 0;                                                                       \
+        st_##SFX(c, i + j * ldc, cplx, r);                                                                  \
+        if (gauge) gauge[i + j * n] = g;                                                                    \
+      }                                                                                                     \
+  }
+
+GEN(float, f)
+GEN(double, d)
+
+/* C := alpha*A*B + beta*C (side 0) or alpha*B*A + beta*C (side 1); A symmetric (herm 0) or Hermitian
+ * (herm 1), only its uplo triangle (0 upper, 1 lower) is read.  alpha/beta: 1 value, 2 for complex. */
+int oracle_symm(int dtype, int herm, int side, int uplo, long m, long n, const void *alpha, const void *a, long lda,
+                const void *b, long ldb, const void *beta, void *c, long ldc, double *gauge) {
+  if (m <= 0 || n <= 0) return 0;
+  int cplx = dtype == OR_C || dtype == OR_Z;
+  if (dtype == OR_S || dtype == OR_C)
+    symm_f(cplx, herm && cplx, side, uplo, m, n, (const float *)alpha, (const float *)a, lda, (const float *)b, ldb,
+           (const float *)beta, (float *)c, ldc, gauge);
+  else if (dtype == OR_D || dtype == OR_Z)
+    symm_d(cplx, herm && cplx, side, uplo, m, n, (const double *)alpha, (const double *)a, lda, (const double *)b, ldb,
+           (const double *)beta, (double *)c, ldc, gauge);
+  else return -1;
+  return 0;
+}
+
+/* rank-k / rank-2k update of the uplo triangle of the n x n matrix C.  trans 0: A (and B) n x k,
+ * 1: k x n.  herm: HERK / HER2K (alpha real for HERK; beta real; alpha and beta are still passed as
+ * (re, im) pairs for complex types).  two: SYR2K / HER2K. */
+int oracle_rankk(int dtype, int herm, int two, int uplo, int trans, long n, long k, const void *alpha, const void *a,
+                 long lda, const void *b, long ldb, const void *beta, void *c, long ldc, double *gauge) {
+  if (n <= 0) return 0;
+  int cplx = dtype == OR_C || dtype == OR_Z;
+  if (dtype == OR_S || dtype == OR_C)
+    rankk_f(cplx, herm && cplx, two, uplo, trans, n, k, (const float *)alpha, (const float *)a, lda, (const float *)b, ldb,
+            (const float *)beta, (float *)c, ldc, gauge);
+  else if (dtype == OR_D || dtype == OR_Z)
+    rankk_d(cplx, herm && cplx, two, uplo, trans, n, k, (const double *)alpha, (const double *)a, lda, (const double *)b, ldb,
+            (const double *)beta, (double *)c, ldc, gauge);
+  else return -1;
+  return 0;
+}
+
+/* ---- argument validation, info value xerbla_ would get or `ok` -------------------------
+ * SYMM/HEMM: interface/symm.c:203-227 (side, uplo in {0, 1, -1}); rank-k family: syrk.c:158-165,
+ * syr2k.c:280-288 (two != 0 adds the ldb check and moves ldc to 12). */
+static long max1(long x) { return x > 1 ? x : 1; }
+int oracle_check_symm(int side, int uplo, long m, long n, long lda, long ldb, long ldc, int ok) {
+  int info = ok;
+  if (ldc < max1(m)) info = 12;
+  if (ldb < max1(m)) info = 9;
+  if (lda < max1(side == 0 ? m : n)) info = 7;
+  if (n < 0) info = 4;
+  if (m < 0) info = 3;
+  if (uplo < 0) info = 2;
+  if (side < 0) info = 1;
+  return info;
+}
+int oracle_check_rankk(int two, int uplo, int trans, long n, long k, long lda, long ldb, long ldc, int ok) {
+  long nrowa = (trans & 1) ? k : n;
+  int info = ok;
+  if (ldc < max1(n)) info = two ? 12 : 10;
+  if (two && ldb < max1(nrowa)) info = 9;
+  if (lda < max1(nrowa)) info = 7;
+  if (k < 0) info = 4;
+  if (n < 0) info = 3;
+  if (trans < 0) info = 2;
+  if (uplo < 0) info = 1;
+  return info;
+}

@@ -43,8 +43,8 @@ for line in open(log, errors="replace"):
     elif depth2:
         rel = next(p for p in (f"driver/level3/{src}", f"driver/others/{src}")
                    if os.path.exists(os.path.join(tree, p)))
-    else:
-        rel = f"interface/{src}"
+    else:   # -I.. : interface/ or a kernel/ sub-directory (kernel/Makefile.L3 names generic/ and $(ARCH)/ sources relatively)
+        rel = next((p for p in (f"interface/{src}", f"kernel/{src}") if os.path.exists(os.path.join(tree, p))), f"interface/{src}")
     assert os.path.exists(os.path.join(tree, rel)), (obj, rel)
     i_ver = next(i for i, t in enumerate(tok) if t.startswith("-DVERSION="))
     i_un = tok.index("-UASMNAME")

@@ -168,3 +168,87 @@ def test_argument_validation_table(oracle):
     assert oracle.check_args(0, 0, 3, 4, 5, 3, 5, 3, -1) == -1
     # OpenBLAS accepts ldc == m == 0 (weaker than Netlib's max(1,m)): interface/gemm.c:276
     assert oracle.check_args(0, 0, 0, 4, 5, 1, 5, 0, 0) == 0
+
+
+# ------------------------------------------------------------------------------------------
+# symmetric level-3 family: oracle/level3_oracle.c pinned BY BOUND
+# ------------------------------------------------------------------------------------------
+def test_level3_oracle_matches_reference_golden_within_bound(oracle):
+    """tests/golden/level3_golden.npz holds outputs of the reference's GENERIC build for every
+    routine / precision / side / uplo / trans combination.  The oracle sums in its own order, so
+    it must agree within c*K*eps*gauge; whatever the routine may not touch must be bit-identical."""
+    import level3_helpers as L
+    g = np.load(os.path.join(ROOT, "tests", "golden", "level3_golden.npz"))
+    meta = g["meta"]
+    assert len(meta) == 144
+    worst = 0.0
+    for idx, row in enumerate(meta):
+        case = L.meta_case(row)
+        a, b, c0, ref_c = g[f"a{idx}"], g[f"b{idx}"], g[f"c0_{idx}"], g[f"c{idx}"]
+        _, want, gauge, K, touched = L.run_case(lambda *args: None, oracle, case, a, b if b.size else a, c0)
+        worst = max(worst, L.check_case(case, ref_c, want, gauge, K, touched, c0))
+    assert worst < 1.0
+
+
+@pytest.mark.skipif(not cpu.have_reference("generic"), reason="oracle/_ref not built")
+def test_level3_oracle_vs_live_reference(oracle):
+    """Same comparison live, including the best SIMD build of the reference, bigger k, NaN in the
+    triangle of A that must not be read and in the part of C that must not be touched."""
+    import level3_helpers as L
+    rng = np.random.default_rng(77)
+    for ref in (cpu.Reference("generic"), cpu.Reference()):
+        ref.set_threads(1)
+        call = L.bind(ref.lib)
+        for dtype in (cpu.S, cpu.D, cpu.CX, cpu.Z):
+            cplx = dtype in (cpu.CX, cpu.Z)
+            for herm in ((0, 1) if cplx else (0,)):
+                for x in (0, 1):
+                    for uplo in (0, 1):
+                        m, n = 45, 38
+                        ka = n if x else m
+                        a, b, c0 = L.operand(rng, dtype, ka, ka + 1), L.operand(rng, dtype, n, m + 2), L.operand(rng, dtype, n, m + 3)
+                        jj, ii = np.meshgrid(np.arange(ka), np.arange(ka + 1), indexing="ij")
+                        a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan      # the other triangle of A
+                        alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
+                        case = (0, dtype, herm, x, uplo, 0, m, n, 0, ka + 1, m + 2, m + 3, alpha, beta)
+                        got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+                        L.check_case(case, got, want, gauge, K, touched, c0)
+                        for trans in (0, 1):
+                            nn, k = 41, 130
+                            rows, cols = (k, nn) if trans else (nn, k)
+                            a, b, c0 = L.operand(rng, dtype, cols, rows + 1), L.operand(rng, dtype, cols, rows + 2), L.operand(rng, dtype, nn, nn + 3)
+                            jj, ii = np.meshgrid(np.arange(nn), np.arange(nn + 3), indexing="ij")
+                            c0[((ii < jj) if uplo else (ii > jj)) & (ii < nn)] = np.nan     # the other triangle of C
+                            al = 0.7 if (herm and not x) or not cplx else 0.7 - 0.9j
+                            be = 1.3 if herm or not cplx else 1.3 - 1.1j
+                            case = (1, dtype, herm, x, uplo, trans, nn, nn, k, rows + 1, rows + 2, nn + 3, al, be)
+                            got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+                            L.check_case(case, got, want, gauge, K, touched, c0)
+
+
+def test_level3_argument_checks_match_reference_error_exits(oracle):
+    """oracle_check_symm / oracle_check_rankk against the info values the REFERENCE reported for
+    the column-major probes of tests/c/errexit_level3.c (tests/golden/errexit_level3_reference.txt)."""
+    want = {}
+    for ln in open(os.path.join(ROOT, "tests", "golden", "errexit_level3_reference.txt")):
+        if ln.startswith("col ") and "info=" in ln:
+            want[ln[4:34].strip()] = int(ln.rsplit("info=", 1)[1])
+    assert oracle.check_symm(-1, 0, 0, 0, 1, 1, 1, -1) == want["dsymm side"] == 1
+    assert oracle.check_symm(0, -1, 0, 0, 1, 1, 1, -1) == want["dsymm uplo"] == 2
+    assert oracle.check_symm(0, 0, -1, 0, 1, 1, 1, -1) == want["dsymm m<0"]
+    assert oracle.check_symm(1, 1, 0, -1, 1, 1, 1, -1) == want["dsymm n<0"]
+    assert oracle.check_symm(0, 0, 2, 0, 1, 2, 2, -1) == want["dsymm lda left"]
+    assert oracle.check_symm(1, 0, 0, 2, 1, 2, 2, -1) == want["dsymm lda right"]
+    assert oracle.check_symm(0, 1, 2, 0, 2, 1, 2, -1) == want["dsymm ldb left m=2"]
+    assert oracle.check_symm(0, 0, 2, 0, 2, 2, 1, -1) == want["dsymm ldc m=2"]
+    assert oracle.check_symm(-1, 0, 2, 3, 2, 2, 1, -1) == want["dsymm side + others"]
+    assert oracle.check_rankk(0, -1, 0, 0, 0, 1, 1, 1, -1) == want["dsyrk uplo"]
+    assert oracle.check_rankk(0, 0, -1, 0, 0, 1, 1, 1, -1) == want["dsyrk trans"]
+    assert oracle.check_rankk(0, 0, 0, -1, 0, 1, 1, 1, -1) == want["dsyrk n<0"]
+    assert oracle.check_rankk(0, 1, 1, 0, -1, 1, 1, 1, -1) == want["dsyrk k<0"]
+    assert oracle.check_rankk(0, 0, 0, 2, 0, 1, 1, 2, -1) == want["dsyrk lda N n=2"]
+    assert oracle.check_rankk(0, 0, 1, 0, 2, 1, 1, 1, -1) == want["dsyrk lda T k=2"]
+    assert oracle.check_rankk(0, 1, 0, 2, 0, 2, 2, 1, -1) == want["dsyrk ldc"] == 10
+    assert oracle.check_rankk(1, 0, 1, 0, 2, 2, 1, 1, -1) == want["dsyr2k ldb T"] == 9
+    assert oracle.check_rankk(1, 1, 0, 2, 0, 2, 2, 1, -1) == want["dsyr2k ldc"] == 12
+    assert oracle.check_rankk(1, 0, 0, 2, 0, 1, 2, 2, -1) == want["dsyr2k lda"] == 7
