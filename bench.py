@@ -417,6 +417,52 @@ def run_sweep(args):
     return rows
 
 
+def run_sweep_level3(args):
+    """Developer view: the symmetric level-3 family on device-resident operands, TFLOP/s with the
+    conventional flop counts (SYMM 2*m*m*n, SYRK n*n*k, SYR2K 2*n*n*k real; complex x4) -- what a GEMM
+    of the same useful work would be credited with."""
+    import ctypes as C
+    import torch
+    import openblas_b200 as ob
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    lib = ob.lib()
+    rows = []
+    i_ = lambda v: C.byref(C.c_int(int(v)))
+    for dtype in [d for d in args.sweep_dtypes.split(",") if d in "sdcz"]:
+        cplx = dtype in "cz"
+        rdt = torch.float64 if dtype in "dz" else torch.float32
+        ct = C.c_double if dtype in "dz" else C.c_float
+        peak, _ = measured_peak(dtype)
+        for nsz in [int(x) for x in args.sizes.split(",")]:
+            n = k = nsz
+            mk = lambda: (torch.rand((nsz, nsz, 2) if cplx else (nsz, nsz), device=dev, dtype=rdt) - 0.5)
+            a, b, c = mk(), mk(), mk()
+            al2, be2 = (ct * 2)(0.7, 0.2), (ct * 2)(1.3, 0.1)
+            alr, ber = ct(0.7), ct(1.3)
+            pa, pb, pc = C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr())
+            jobs = [("symm", lambda: getattr(lib, dtype + "symm_")(C.c_char_p(b"L"), C.c_char_p(b"U"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
+                    ("syrk", lambda: getattr(lib, dtype + "syrk_")(C.c_char_p(b"L"), C.c_char_p(b"N"), i_(n), i_(k), al2, pa, i_(n), be2, pc, i_(n)), 1.0),
+                    ("syr2k", lambda: getattr(lib, dtype + "syr2k_")(C.c_char_p(b"U"), C.c_char_p(b"T"), i_(n), i_(k), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0)]
+            if cplx:
+                jobs += [("hemm", lambda: getattr(lib, dtype + "hemm_")(C.c_char_p(b"R"), C.c_char_p(b"L"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
+                         ("herk", lambda: getattr(lib, dtype + "herk_")(C.c_char_p(b"U"), C.c_char_p(b"C"), i_(n), i_(k), C.byref(alr), pa, i_(n), C.byref(ber), pc, i_(n)), 1.0)]
+            for name, f, factor in jobs:
+                f(); torch.cuda.synchronize()
+                reps = 3
+                t0 = time.perf_counter()                      # the BLAS call is synchronous: wall time of the call itself
+                for _ in range(reps):
+                    f()
+                ms = (time.perf_counter() - t0) / reps * 1e3
+                tf = factor * (4.0 if cplx else 1.0) * nsz ** 3 / (ms * 1e-3) / 1e12
+                rows.append({"routine": dtype + name, "n": nsz, "k": nsz, "ms": ms, "tflops_useful": tf, "frac_of_gemm_peak": tf / peak,
+                             "launches_per_call": None})
+                l0 = ob.cblas.launch_count(); f(); rows[-1]["launches_per_call"] = int(ob.cblas.launch_count() - l0)
+                print(json.dumps(rows[-1]), flush=True)
+            del a, b, c
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,11 +476,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true"); ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sweep", action="store_true"); ap.add_argument("--sizes", default="1024,2048,4096,8192,16384")
+    ap.add_argument("--sweep-level3", action="store_true", help="developer view: SYMM/SYRK/SYR2K/HEMM/HERK on device operands")
     ap.add_argument("--sweep-dtypes", default="d,s,z,c,sb")
     ap.add_argument("--all-ops", action="store_true", help="sweep: all four N/T combinations at every size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.sweep_level3:
+        return run_sweep_level3(args)
     if args.sweep:
         return run_sweep(args)
     return run_gpu(args)

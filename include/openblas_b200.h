@@ -41,6 +41,7 @@ typedef CBLAS_ORDER CBLAS_LAYOUT;
 /* cblas.h:64-66 */
 typedef enum CBLAS_UPLO      {CblasUpper = 121, CblasLower = 122} CBLAS_UPLO;
 typedef enum CBLAS_SIDE      {CblasLeft = 141, CblasRight = 142} CBLAS_SIDE;
+typedef enum CBLAS_DIAG      {CblasNonUnit = 131, CblasUnit = 132} CBLAS_DIAG;
 #endif
 
 /* =====================================================================================
@@ -207,6 +208,43 @@ void cher2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, float *alpha, floa
              float *beta, float *c, blasint *ldC);
 void zher2k_(char *UPLO, char *TRANS, blasint *N, blasint *K, double *alpha, double *a, blasint *ldA, double *b, blasint *ldB,
              double *beta, double *c, blasint *ldC);
+
+/* ---- TRMM / TRSM (cblas.h:347-363; common_interface.h:530-552; bodies interface/trsm.c:96-430, which the
+ *      reference compiles twice, with and without -DTRMM).  B := alpha*op(A)*B or alpha*B*op(A) (TRMM), or the
+ *      solution X of op(A)*X = alpha*B or X*op(A) = alpha*B (TRSM); A triangular, only its uplo triangle is read
+ *      and a unit diagonal is never read. */
+void cblas_strmm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, float alpha, const float *A, blasint lda, float *B, blasint ldb);
+void cblas_dtrmm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, double alpha, const double *A, blasint lda, double *B, blasint ldb);
+void cblas_ctrmm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, const void *alpha, const void *A, blasint lda, void *B, blasint ldb);
+void cblas_ztrmm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, const void *alpha, const void *A, blasint lda, void *B, blasint ldb);
+void cblas_strsm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, float alpha, const float *A, blasint lda, float *B, blasint ldb);
+void cblas_dtrsm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, double alpha, const double *A, blasint lda, double *B, blasint ldb);
+void cblas_ctrsm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, const void *alpha, const void *A, blasint lda, void *B, blasint ldb);
+void cblas_ztrsm(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                 enum CBLAS_DIAG Diag, blasint M, blasint N, const void *alpha, const void *A, blasint lda, void *B, blasint ldb);
+void strmm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA,
+            float *b, blasint *ldB);
+void dtrmm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA,
+            double *b, blasint *ldB);
+void ctrmm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA,
+            float *b, blasint *ldB);
+void ztrmm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA,
+            double *b, blasint *ldB);
+void strsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA,
+            float *b, blasint *ldB);
+void dtrsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA,
+            double *b, blasint *ldB);
+void ctrsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, float *alpha, float *a, blasint *ldA,
+            float *b, blasint *ldB);
+void ztrsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA,
+            double *b, blasint *ldB);
 
 /* ---- bf16 conversion helpers callers of sbgemm need (cblas.h:433-440;
  *      interface/tobf16.c, interface/bf16to.c; rounding rule kernel/x86_64/tobf16.c:46-96) */

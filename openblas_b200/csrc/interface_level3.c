@@ -1,8 +1,8 @@
 /*
- * interface_level3.c -- BLAS / CBLAS entry points of the symmetric level-3 family, host side,
- * plain C: SYMM / HEMM, SYRK / HERK, SYR2K / HER2K for s, d, c, z.
+ * interface_level3.c -- BLAS / CBLAS entry points of the rest of level 3, host side, plain C:
+ * SYMM / HEMM, SYRK / HERK, SYR2K / HER2K and TRMM / TRSM for s, d, c, z.
  *
- * Replaces the reference's interface/symm.c, interface/syrk.c and interface/syr2k.c (each
+ * Replaces the reference's interface/symm.c, interface/syrk.c, interface/syr2k.c and interface/trsm.c (each
  * compiled there once per precision, ABI and -DHEMM).  One table-driven implementation serves
  * all of them; an entry point only decodes its flag arguments and packs the rest.  What is
  * restated from the reference:
@@ -136,6 +136,57 @@ static void rankk_entry(const char *name, int routine, int dtype, int cblas, int
   run(&p, name);
 }
 
+/* ---------------------------------------------------------------- TRMM / TRSM ---- */
+static int diag_of_char(char ch) { ch = upper(ch); return ch == 'U' ? 1 : ch == 'N' ? 0 : -1; }   /* 1 = unit */
+static int diag_of_cblas(int d) { return d == CblasUnit ? 1 : d == CblasNonUnit ? 0 : -1; }
+static int op_of_char(char ch, int cplx) {        /* trsm.c:172-175: N, T, R, C for every type; real types fold R->N, C->T */
+  ch = upper(ch);
+  return ch == 'N' ? B200_N : ch == 'T' ? B200_T : ch == 'R' ? (cplx ? B200_R : B200_N) : ch == 'C' ? (cplx ? B200_C_ : B200_T) : -1;
+}
+static int op_of_cblas(int t, int cplx) {         /* trsm.c:283-291 */
+  return t == CblasNoTrans ? B200_N : t == CblasTrans ? B200_T : t == CblasConjNoTrans ? (cplx ? B200_R : B200_N)
+       : t == CblasConjTrans ? (cplx ? B200_C_ : B200_T) : -1;
+}
+
+/* interface/trsm.c: the checks (:188-197, :296-305); row-major swaps m and n and flips side and uplo
+ * but not trans (:308-333); the Fortran entry hands xerbla_ sizeof(ERROR_NAME)-1 = 6 (:207), the CBLAS
+ * one sizeof(ERROR_NAME) = 7 (:354); quick return m == 0 or n == 0 (:359). */
+static void trxm_entry(const char *name, int routine, int dtype, int cblas, int order, int side, int uplo, int trans, int unit,
+                       int64_t m, int64_t n, const double alpha[2], const void *a, int64_t lda, void *b, int64_t ldb) {
+  blasint info = cblas ? -1 : 0;
+  if (cblas && order == CblasRowMajor) {
+    side = flip(side); uplo = flip(uplo);
+    int64_t t = m; m = n; n = t;
+  } else if (cblas && order != CblasColMajor) {
+    report(name, 0);
+    return;
+  }
+  const int64_t nrowa = (side & 1) ? n : m;
+  if (ldb < max1(m)) info = 11;
+  if (lda < max1(nrowa)) info = 9;
+  if (n < 0) info = 6;
+  if (m < 0) info = 5;
+  if (unit < 0) info = 4;
+  if (trans < 0) info = 3;
+  if (uplo < 0) info = 2;
+  if (side < 0) info = 1;
+  if (cblas ? info >= 0 : info != 0) {
+    char nm[8];
+    memcpy(nm, name, 7);
+    xerbla_(nm, &info, cblas ? 7 : 6);
+    return;
+  }
+  if (m == 0 || n == 0) return;
+
+  b200_l3_problem p;
+  memset(&p, 0, sizeof p);
+  p.routine = routine; p.dtype = dtype; p.side = side; p.uplo = uplo; p.trans = trans; p.unit = unit;
+  p.m = m; p.n = n; p.lda = lda; p.ldb = ldb; p.ldc = ldb;
+  p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = 0.0; p.beta[1] = 0.0;
+  p.a = a; p.b = NULL; p.c = b;
+  run(&p, name);
+}
+
 /* ---------------------------------------------------------------- entry points ---- */
 #define REAL2(x)  {(double)(x), 0.0}
 #define CPLX2(T, p) {(double)((const T *)(p))[0], (double)((const T *)(p))[1]}
@@ -209,3 +260,26 @@ DEF_SYR2K(csyr2k, "CSYR2K", B200_SYR2K, B200_C, 1, void, const void *, const voi
 DEF_SYR2K(zsyr2k, "ZSYR2K", B200_SYR2K, B200_Z, 1, void, const void *, const void *, SC_CD, SC_CD, double)
 DEF_SYR2K(cher2k, "CHER2K", B200_HER2K, B200_C, 2, void, const void *, float, SC_CF, SC_REAL, float)
 DEF_SYR2K(zher2k, "ZHER2K", B200_HER2K, B200_Z, 2, void, const void *, double, SC_CD, SC_REAL, double)
+
+#define DEF_TRXM(P, NAME, ROUTINE, DTYPE, CPLX, T, CS, CSCAL, FSCAL)                                                  \
+  B200_EXPORT void cblas_##P(enum CBLAS_ORDER Order, enum CBLAS_SIDE Side, enum CBLAS_UPLO Uplo,                      \
+                             enum CBLAS_TRANSPOSE TransA, enum CBLAS_DIAG Diag, blasint M, blasint N, CS alpha,       \
+                             const T *A, blasint lda, T *B, blasint ldb) {                                            \
+    const double al[2] = CSCAL(alpha);                                                                               \
+    trxm_entry(NAME, ROUTINE, DTYPE, 1, (int)Order, side_of_cblas((int)Side), uplo_of_cblas((int)Uplo),              \
+               op_of_cblas((int)TransA, CPLX), diag_of_cblas((int)Diag), M, N, al, A, lda, B, ldb);                  \
+  }                                                                                                                  \
+  B200_EXPORT void P##_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, FSCAL *alpha,       \
+                        FSCAL *a, blasint *ldA, FSCAL *b, blasint *ldB) {                                             \
+    const double al[2] = F_##CSCAL(alpha);                                                                           \
+    trxm_entry(NAME, ROUTINE, DTYPE, 0, 0, side_of_char(*SIDE), uplo_of_char(*UPLO), op_of_char(*TRANSA, CPLX),      \
+               diag_of_char(*DIAG), *M, *N, al, a, *ldA, b, *ldB);                                                   \
+  }
+DEF_TRXM(strmm, "STRMM ", B200_TRMM, B200_S, 0, float, float, SC_REAL, float)
+DEF_TRXM(dtrmm, "DTRMM ", B200_TRMM, B200_D, 0, double, double, SC_REAL, double)
+DEF_TRXM(ctrmm, "CTRMM ", B200_TRMM, B200_C, 1, void, const void *, SC_CF, float)
+DEF_TRXM(ztrmm, "ZTRMM ", B200_TRMM, B200_Z, 1, void, const void *, SC_CD, double)
+DEF_TRXM(strsm, "STRSM ", B200_TRSM, B200_S, 0, float, float, SC_REAL, float)
+DEF_TRXM(dtrsm, "DTRSM ", B200_TRSM, B200_D, 0, double, double, SC_REAL, double)
+DEF_TRXM(ctrsm, "CTRSM ", B200_TRSM, B200_C, 1, void, const void *, SC_CF, float)
+DEF_TRXM(ztrsm, "ZTRSM ", B200_TRSM, B200_Z, 1, void, const void *, SC_CD, double)

@@ -74,6 +74,127 @@ __global__ void __launch_bounds__(256) tri_merge_kernel(int uplo, int herm, int6
   }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * tri_block_kernel: the base case of the recursive TRMM / TRSM (runtime_level3.inl).  One CTA of 64
+ * threads takes one nb x nb (nb <= 64) diagonal block E and up to 64 right-hand sides, one per
+ * thread, both staged in shared memory:
+ *     SOLVE = false   x := alpha * E x         (rows bottom-up for a lower E, so it works in place)
+ *     SOLVE = true    x := E^-1 (alpha * x)    by forward / backward substitution -- the reference's
+ *                     trsm kernels substitute too (kernel/generic/trsm_kernel_LN.c `solve`), no
+ *                     explicit inverse of the block is formed
+ * E(i,k) = cj(F[i*fs_i + k*fs_k]) lets the host describe op(F) (left side) or op(F)^T (right side:
+ * X E = alpha B  <=>  E^T X^T = alpha B^T); element r of right-hand side c lives at B[r*rs + c*cs].
+ * Loads and stores walk whichever index is contiguous in memory.  E(i,k) reads are warp broadcasts,
+ * X(k, thread) reads hit consecutive banks. */
+template <class T> __device__ __forceinline__ T t_zero() { T v; memset(&v, 0, sizeof v); return v; }
+template <class T> __device__ __forceinline__ T t_one() { T v; memset(&v, 0, sizeof v); *reinterpret_cast<decltype(v.x) *>(&v) = 1; return v; }
+template <> __device__ __forceinline__ float t_one<float>() { return 1.f; }
+template <> __device__ __forceinline__ double t_one<double>() { return 1.0; }
+__device__ __forceinline__ float t_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ double t_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ float2 t_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 t_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float t_add(float a, float b) { return a + b; }
+__device__ __forceinline__ double t_add(double a, double b) { return a + b; }
+__device__ __forceinline__ float2 t_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 t_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float t_sub(float a, float b) { return a - b; }
+__device__ __forceinline__ double t_sub(double a, double b) { return a - b; }
+__device__ __forceinline__ float2 t_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 t_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float t_div(float a, float b) { return a / b; }
+__device__ __forceinline__ double t_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float2 t_div(float2 a, float2 b) {
+  float d = b.x * b.x + b.y * b.y;
+  return make_float2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+__device__ __forceinline__ double2 t_div(double2 a, double2 b) {
+  double d = b.x * b.x + b.y * b.y;
+  return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+template <class T, class R> __device__ __forceinline__ T t_scalar(R re, R im) {
+  if constexpr (Cx<T>::value) { T v; v.x = re; v.y = im; return v; } else { return (T)re; }
+}
+
+constexpr int TRI_NB = 64;      /* largest diagonal block; also the number of right-hand sides per CTA */
+
+template <class T, class R, bool SOLVE>
+__global__ void __launch_bounds__(TRI_NB) tri_block_kernel(int nb, int64_t nrhs, int eff_lower, int unit, int cj, const T *__restrict__ f,
+                                                           int64_t fs_i, int64_t fs_k, R ar, R ai, T *__restrict__ b, int64_t rs, int64_t cs) {
+  extern __shared__ __align__(16) unsigned char tri_smem[];
+  constexpr int LD = TRI_NB + 1;
+  T *E = reinterpret_cast<T *>(tri_smem);
+  T *X = E + TRI_NB * LD;
+  const int t = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * TRI_NB;
+  for (int idx = t; idx < nb * nb; idx += TRI_NB) {
+    const int i = fs_i == 1 ? idx % nb : idx / nb, k = fs_i == 1 ? idx / nb : idx % nb;
+    T v = t_zero<T>();
+    if (i == k) v = unit ? t_one<T>() : f[i * fs_i + k * fs_k];
+    else if (eff_lower ? (k < i) : (k > i)) v = f[i * fs_i + k * fs_k];
+    if (cj) v = conj_of(v);
+    E[i * LD + k] = v;
+  }
+  for (int idx = t; idx < nb * TRI_NB; idx += TRI_NB) {
+    const int r = rs == 1 ? idx % nb : idx / TRI_NB, c = rs == 1 ? idx / nb : idx % TRI_NB;
+    X[r * LD + c] = (c0 + c < nrhs) ? b[r * rs + (c0 + c) * cs] : t_zero<T>();
+  }
+  __syncthreads();
+  if (c0 + t < nrhs) {
+    const T alpha = t_scalar<T, R>(ar, ai);
+    if (!SOLVE) {
+      if (eff_lower) {
+        for (int i = nb - 1; i >= 0; i--) {
+          T acc = t_zero<T>();
+          for (int k = 0; k <= i; k++) acc = t_add(acc, t_mul(E[i * LD + k], X[k * LD + t]));
+          X[i * LD + t] = t_mul(alpha, acc);
+        }
+      } else {
+        for (int i = 0; i < nb; i++) {
+          T acc = t_zero<T>();
+          for (int k = i; k < nb; k++) acc = t_add(acc, t_mul(E[i * LD + k], X[k * LD + t]));
+          X[i * LD + t] = t_mul(alpha, acc);
+        }
+      }
+    } else {
+      if (eff_lower) {
+        for (int i = 0; i < nb; i++) {
+          T acc = t_mul(alpha, X[i * LD + t]);
+          for (int k = 0; k < i; k++) acc = t_sub(acc, t_mul(E[i * LD + k], X[k * LD + t]));
+          X[i * LD + t] = unit ? acc : t_div(acc, E[i * LD + i]);
+        }
+      } else {
+        for (int i = nb - 1; i >= 0; i--) {
+          T acc = t_mul(alpha, X[i * LD + t]);
+          for (int k = i + 1; k < nb; k++) acc = t_sub(acc, t_mul(E[i * LD + k], X[k * LD + t]));
+          X[i * LD + t] = unit ? acc : t_div(acc, E[i * LD + i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = t; idx < nb * TRI_NB; idx += TRI_NB) {
+    const int r = rs == 1 ? idx % nb : idx / TRI_NB, c = rs == 1 ? idx / nb : idx % TRI_NB;
+    if (c0 + c < nrhs) b[r * rs + (c0 + c) * cs] = X[r * LD + c];
+  }
+}
+
+template <class T, class R, bool SOLVE>
+cudaError_t tri_block_t(int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i, int64_t fs_k, double ar,
+                        double ai, void *b, int64_t rs, int64_t cs, cudaStream_t s) {
+  static bool configured = false;
+  auto kern = tri_block_kernel<T, R, SOLVE>;
+  const size_t smem = 2 * (size_t)TRI_NB * (TRI_NB + 1) * sizeof(T);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<(unsigned)((nrhs + TRI_NB - 1) / TRI_NB), TRI_NB, smem, s>>>(nb, nrhs, eff_lower, unit, cj, (const T *)f, fs_i, fs_k, (R)ar, (R)ai,
+                                                                       (T *)b, rs, cs);
+  return cudaGetLastError();
+}
+
 template <class T>
 cudaError_t expand_t(int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out, int64_t ldo, cudaStream_t s) {
   const int64_t tiles = ((n + 31) / 32) * ((n + 7) / 8);
@@ -104,6 +225,25 @@ cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, co
     default: return cudaErrorNotSupported;
   }
   if (e == cudaSuccess) count_launch("expand_symmetric");
+  return e;
+}
+
+cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,
+                             int64_t fs_k, double ar, double ai, void *b, int64_t rs, int64_t cs, cudaStream_t stream) {
+  if (nb <= 0 || nrhs <= 0) return cudaSuccess;
+  if (nb > TRI_NB) return cudaErrorInvalidValue;
+  cudaError_t e;
+#define TRI_CASE(T, R) (solve ? tri_block_t<T, R, true>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream) \
+                              : tri_block_t<T, R, false>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream))
+  switch (dtype) {
+    case B200_S: e = TRI_CASE(float, float); break;
+    case B200_D: e = TRI_CASE(double, double); break;
+    case B200_C: e = TRI_CASE(float2, float); break;
+    case B200_Z: e = TRI_CASE(double2, double); break;
+    default: return cudaErrorNotSupported;
+  }
+#undef TRI_CASE
+  if (e == cudaSuccess) count_launch(solve ? "tri_block_solve" : "tri_block_multiply");
   return e;
 }
 

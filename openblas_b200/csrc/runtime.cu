@@ -601,8 +601,9 @@ B200_HIDDEN int b200_run_problem(const b200_problem *p) {
 B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
   {  /* nothing to do (alpha == 0 or k == 0 with beta == 1): return before CUDA is touched */
     const bool symm = p->routine == B200_SYMM || p->routine == B200_HEMM;
-    const bool product = !(p->alpha[0] == 0.0 && p->alpha[1] == 0.0) && (symm || p->k > 0);
-    if (!product && p->beta[0] == 1.0 && p->beta[1] == 0.0) return 0;
+    const bool trxm = p->routine == B200_TRMM || p->routine == B200_TRSM;
+    const bool product = !(p->alpha[0] == 0.0 && p->alpha[1] == 0.0) && (symm || trxm || p->k > 0);
+    if (!trxm && !product && p->beta[0] == 1.0 && p->beta[1] == 0.0) return 0;
   }
   ContextLease lease;
   int err = acquire(&lease.c);

@@ -30,6 +30,63 @@ static cudaError_t gemm_on_device(int dtype, int ta, int tb, int64_t m, int64_t 
 
 static int64_t rankk_block(int64_t n) { return n >= 4096 ? 512 : n >= 1024 ? 256 : 128; }
 
+/* ---- TRMM / TRSM: recursive splitting of the triangular matrix E = op(A) ------------------------
+ * (the reference blocks the same routines over its GEMM kernel: driver/level3/trmm_L.c, trmm_R.c,
+ * trsm_L.c, trsm_R.c).  E is cut at a multiple of 64 near the middle; the off-diagonal block is ONE
+ * GEMM with a large inner dimension (that is where the flops are), the two diagonal halves recurse,
+ * 64 x 64 diagonal blocks go to tri_block_kernel.  The order of the three steps is what makes the
+ * update valid in place:
+ *   TRMM  left,  E lower:  B2 := a E22 B2;  B2 += a E21 B1;  B1 := a E11 B1      (upper: mirrored)
+ *   TRMM  right, E lower:  B1 := a B1 E11;  B1 += a B2 E21;  B2 := a B2 E22
+ *   TRSM  left,  E lower:  X1 = a E11^-1 B1;  B2 := a B2 - E21 X1;  X2 = E22^-1 B2
+ *   TRSM  right, E lower:  X2 = a B2 E22^-1;  B1 := a B1 - X2 E21;  X1 = B1 E11^-1 */
+struct TriWork {
+  int dtype, op; bool solve, left, eff_lower, unit;
+  const char *a; int64_t lda; char *b; int64_t ldb; int64_t m, n; size_t es; cudaStream_t s;
+  /* rows [r0, ..) x cols [c0, ..) of E as a GEMM operand that still needs `op` applied */
+  const char *eblk(int64_t r0, int64_t c0) const { return a + ((op & 1) ? ((size_t)c0 + (size_t)r0 * lda) : ((size_t)r0 + (size_t)c0 * lda)) * es; }
+  char *bpart(int64_t off) const { return b + (left ? (size_t)off : (size_t)off * ldb) * es; }   /* rows (left) or columns (right) from off */
+};
+
+/* B(dst part) := beta * B(dst part) + alpha * [E(r0.., c0..) applied to B(src part)] */
+static cudaError_t tri_gemm(const TriWork &w, int64_t r0, int64_t nr, int64_t c0, int64_t nc, double ar, double ai, double br, double bi) {
+  if (w.left)    /* E block (nr x nc) times rows c0.. of B into rows r0.. */
+    return gemm_on_device(w.dtype, w.op, B200_N, nr, w.n, nc, ar, ai, w.eblk(r0, c0), w.lda, w.bpart(c0), w.ldb, br, bi, w.bpart(r0), w.ldb, w.s);
+  /* columns r0.. of B times E block (nr x nc) into columns c0.. */
+  return gemm_on_device(w.dtype, B200_N, w.op, w.m, nc, nr, ar, ai, w.bpart(r0), w.ldb, w.eblk(r0, c0), w.lda, br, bi, w.bpart(c0), w.ldb, w.s);
+}
+
+static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, double ai) {
+  if (size <= 64) {
+    const bool tr = (w.op & 1) != 0;
+    /* left: E(i,k) = op(F)(i,k); right: the kernel works on E^T */
+    const int64_t fs_i = (w.left ? tr : !tr) ? w.lda : 1, fs_k = (w.left ? tr : !tr) ? 1 : w.lda;
+    CK(launch_tri_block(w.dtype, w.solve, (int)size, w.left ? w.n : w.m, w.left ? w.eff_lower : !w.eff_lower, w.unit, w.op >= 2,
+                        w.a + ((size_t)off + (size_t)off * w.lda) * w.es, fs_i, fs_k, ar, ai, w.bpart(off), w.left ? 1 : w.ldb,
+                        w.left ? w.ldb : 1, w.s));
+    return 0;
+  }
+  const int64_t s1 = ((size / 2 + 63) / 64) * 64, s2 = size - s1, o2 = off + s1;
+  int err;
+  /* which half must be finished first, and which off-diagonal block links them */
+  const bool lower_first_is_2 = w.solve ? !w.left : w.left;     /* for E lower: does part 2 go first? */
+  const bool part2_first = w.eff_lower ? lower_first_is_2 : !lower_first_is_2;
+  const int64_t fo = part2_first ? o2 : off, fs = part2_first ? s2 : s1;      /* first part */
+  const int64_t lo = part2_first ? off : o2, ls = part2_first ? s1 : s2;      /* last part */
+  if (!w.solve) {
+    /* the first part's product reads the OTHER part's original data in the GEMM, so: first part's own
+     * diagonal product, then the coupling GEMM into it, then the other part's diagonal product */
+    if ((err = tri_recurse(w, fo, fs, ar, ai))) return err;
+    if (w.left) CK(tri_gemm(w, fo, fs, lo, ls, ar, ai, 1.0, 0.0));     /* B_first += a E(first, last) B_last */
+    else        CK(tri_gemm(w, lo, ls, fo, fs, ar, ai, 1.0, 0.0));     /* B_first += a B_last E(last, first) */
+    return tri_recurse(w, lo, ls, ar, ai);
+  }
+  if ((err = tri_recurse(w, fo, fs, ar, ai))) return err;               /* X_first */
+  if (w.left) CK(tri_gemm(w, lo, ls, fo, fs, -1.0, 0.0, ar, ai));        /* B_last := a B_last - E(last, first) X_first */
+  else        CK(tri_gemm(w, fo, fs, lo, ls, -1.0, 0.0, ar, ai));        /* B_last := a B_last - X_first E(first, last) */
+  return tri_recurse(w, lo, ls, 1.0, 0.0);
+}
+
 /* everything on the device, pointers are device pointers; scratch holds the expanded operand
  * (SYMM/HEMM) or one NB x NB tile (the others) */
 static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda, const char *b, int64_t ldb, char *c,
@@ -49,6 +106,18 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
     if (!p->side) CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->m, ar, ai, scratch, ldf, b, ldb, br, bi, c, ldc, s));
     else CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->n, ar, ai, b, ldb, scratch, ldf, br, bi, c, ldc, s));
     return 0;
+  }
+
+  if (p->routine == B200_TRMM || p->routine == B200_TRSM) {
+    if (alpha_zero) {                  /* B := 0, exact zeros, B not read (the reference's GEMM_BETA pass, trsm_L.c:101-106) */
+      CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, 0, 0.0, 0.0, c, ldc, c, ldc, 0.0, 0.0, c, ldc, s));
+      return 0;
+    }
+    TriWork w;
+    w.dtype = p->dtype; w.op = p->trans; w.solve = p->routine == B200_TRSM; w.left = !p->side;
+    w.eff_lower = (p->uplo != 0) != ((p->trans & 1) != 0); w.unit = p->unit != 0;
+    w.a = a; w.lda = lda; w.b = c; w.ldb = ldc; w.m = p->m; w.n = p->n; w.es = es; w.s = s;
+    return tri_recurse(w, 0, p->side ? p->n : p->m, ar, ai);
   }
 
   const bool herm = p->routine == B200_HERK || p->routine == B200_HER2K;
@@ -92,16 +161,17 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
 
 static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   const size_t es = b200_in_size(p->dtype);
+  const bool trxm = p->routine == B200_TRMM || p->routine == B200_TRSM;
   const bool symm = p->routine == B200_SYMM || p->routine == B200_HEMM;
   const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
   const bool alpha_zero = p->alpha[0] == 0.0 && p->alpha[1] == 0.0;
   const bool beta_one = p->beta[0] == 1.0 && p->beta[1] == 0.0, beta_zero = p->beta[0] == 0.0 && p->beta[1] == 0.0;
-  const bool product = !alpha_zero && (symm || p->k > 0);
-  if (!product && beta_one) return 0;
+  const bool product = !alpha_zero && (symm || trxm || p->k > 0);
+  if (!product && beta_one && !trxm) return 0;
 
   Operand A, B, C;
   A.es = B.es = C.es = es;
-  if (symm) {
+  if (symm || trxm) {
     const int64_t ka = p->side ? p->n : p->m;
     A.rows = A.cols = ka; B.rows = p->m; B.cols = p->n;
   } else {
@@ -129,7 +199,7 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
     need += round_up(o.bytes_dev(), 256);
   }
   size_t scratch_bytes = 0;
-  if (product) {
+  if (product && !trxm) {
     const int64_t edge = symm ? A.rows : rankk_block(p->n);
     scratch_bytes = round_up(round_up((size_t)edge * es, 128) * (size_t)edge, 256);
   }
@@ -147,7 +217,7 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   cudaStream_t s = ctx->stream;
   /* C goes up unless it is written in full without being read (SYMM/HEMM with beta == 0): the
    * triangular routines bring the whole rectangle back, so the untouched triangle must be there */
-  const bool c_up = !(symm && beta_zero);
+  const bool c_up = trxm ? product : !(symm && beta_zero);
   const bool small = need > 0 && need <= kSmallBytes;
   if (small) {
     if ((err = reserve_pinned(ctx, need))) return err;

@@ -52,19 +52,21 @@ B200_HIDDEN int b200_run_batch(const b200_problem *p, int64_t count);
 
 /* One normalised (column-major) problem of the symmetric level-3 family; the
  * analogue of blas_arg_t as interface/symm.c / syrk.c / syr2k.c fill it. */
-enum b200_l3_routine { B200_SYMM = 0, B200_HEMM, B200_SYRK, B200_HERK, B200_SYR2K, B200_HER2K };
+enum b200_l3_routine { B200_SYMM = 0, B200_HEMM, B200_SYRK, B200_HERK, B200_SYR2K, B200_HER2K, B200_TRMM, B200_TRSM };
 typedef struct b200_l3_problem {
   int routine;          /* enum b200_l3_routine */
   int dtype;            /* enum b200_dtype (S, D, C, Z) */
   int side;             /* SYMM/HEMM: 0 = C := alpha*A*B + beta*C, 1 = C := alpha*B*A + beta*C */
   int uplo;             /* 0 = upper, 1 = lower: triangle of A (SYMM/HEMM) or of C (the others) */
-  int trans;            /* SYRK family: 0 = A (and B) are n x k, 1 = k x n (T, or C for HERK/HER2K) */
+  int trans;            /* SYRK family: 0 = A (and B) are n x k, 1 = k x n (T, or C for HERK/HER2K);
+                           TRMM/TRSM: enum b200_trans of op(A) */
+  int unit;             /* TRMM/TRSM: 1 = unit diagonal (never read) */
   int64_t m, n, k;      /* SYMM/HEMM: C is m x n; SYRK family: C is n x n */
   int64_t lda, ldb, ldc;
   double alpha[2], beta[2];   /* by value; real scalars and HERK's real alpha/beta have im = 0 */
-  const void *a;        /* the symmetric / Hermitian matrix (SYMM/HEMM), else A */
+  const void *a;        /* the symmetric / Hermitian / triangular matrix (SYMM/HEMM/TRMM/TRSM), else A */
   const void *b;        /* the m x n matrix (SYMM/HEMM), B (SYR2K/HER2K), unused otherwise */
-  void *c;
+  void *c;              /* TRMM/TRSM: the m x n matrix B, overwritten (ldc = its leading dimension) */
 } b200_l3_problem;
 
 /* Synchronous solve; pointers may be host or device (runtime.cu). */

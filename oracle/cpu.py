@@ -74,6 +74,13 @@ class Oracle:
         L.oracle_rankk.restype = C.c_int
         L.oracle_rankk.argtypes = [C.c_int] * 5 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
                                                    C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_trxm.restype = C.c_int
+        L.oracle_trxm.argtypes = [C.c_int] * 6 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_trsm_residual.restype = C.c_double
+        L.oracle_trsm_residual.argtypes = [C.c_int] * 5 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                                            C.c_void_p, C.c_long]
+        L.oracle_check_trxm.restype = C.c_int
+        L.oracle_check_trxm.argtypes = [C.c_int] * 4 + [C.c_long] * 4 + [C.c_int]
         L.oracle_check_symm.restype = C.c_int
         L.oracle_check_symm.argtypes = [C.c_int, C.c_int] + [C.c_long] * 5 + [C.c_int]
         L.oracle_check_rankk.restype = C.c_int
@@ -120,6 +127,21 @@ class Oracle:
         assert self.lib.oracle_rankk(dtype, herm, two, uplo, trans, n, k, _ptr(al), _ptr(a), lda, _ptr(b if two else a),
                                      ldb if two else lda, _ptr(be), _ptr(c), ldc, _ptr(g)) == 0
         return g
+
+    def trxm(self, dtype, solve, side, uplo, trans, unit, m, n, alpha, a, lda, b, ldb):
+        """TRMM (solve=0) / TRSM (solve=1) in place on b; returns the m x n gauge of the product form."""
+        al = scalar_bytes(dtype, alpha)
+        g = np.zeros((max(n, 1), max(m, 1)), dtype=np.float64)
+        assert self.lib.oracle_trxm(dtype, solve, side, uplo, trans, unit, m, n, _ptr(al), _ptr(a), lda, _ptr(b), ldb, _ptr(g)) == 0
+        return g
+
+    def trsm_residual(self, dtype, side, uplo, trans, unit, m, n, alpha, a, lda, b0, ldb0, x, ldx):
+        """ctest's acceptance ratio of a TRSM solution x (c_dblat3.f:1195-1235): passes below 16."""
+        al = scalar_bytes(dtype, alpha)
+        return self.lib.oracle_trsm_residual(dtype, side, uplo, trans, unit, m, n, _ptr(al), _ptr(a), lda, _ptr(b0), ldb0, _ptr(x), ldx)
+
+    def check_trxm(self, side, uplo, trans, unit, m, n, lda, ldb, ok):
+        return self.lib.oracle_check_trxm(side, uplo, trans, unit, m, n, lda, ldb, ok)
 
     def check_symm(self, side, uplo, m, n, lda, ldb, ldc, ok):
         return self.lib.oracle_check_symm(side, uplo, m, n, lda, ldb, ldc, ok)
@@ -199,6 +221,16 @@ def call_rankk(lib, dtype, herm, two, uplo, trans, n, k, alpha, a, lda, b, ldb, 
         args += [_ptr(b), i(ldb)]
     fn(*(args + [_ptr(be), _ptr(c), i(ldc)]))
     return c
+
+
+def call_trxm(lib, dtype, solve, side, uplo, trans, unit, m, n, alpha, a, lda, b, ldb):
+    """?trmm_ / ?trsm_ (common_interface.h:530-552) of any library; trans 0..3 = N, T, R, C."""
+    fn = getattr(lib, DTYPE_NAMES[dtype] + ("trsm_" if solve else "trmm_"))
+    al = scalar_bytes(dtype, alpha)
+    i = lambda v: C.byref(C.c_int(int(v)))
+    fn(C.c_char_p(b"LR"[side:side + 1]), C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(b"NTRC"[trans:trans + 1]),
+       C.c_char_p(b"NU"[unit:unit + 1]), i(m), i(n), _ptr(al), _ptr(a), i(lda), _ptr(b), i(ldb))
+    return b
 
 
 class Reference:

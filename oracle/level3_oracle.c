@@ -122,6 +122,73 @@ enum { OR_S = 0, OR_D = 1, OR_C = 2, OR_Z = 3 };
 GEN(float, f)
 GEN(double, d)
 
+/* TRMM / TRSM.  E = op(A) restricted to its triangle, unit diagonal taken as 1 without reading A:
+ * reference/dtrmmf.f:206-355, dtrsmf.f:237-407 (ztrmmf.f / ztrsmf.f for the conjugated forms).
+ * TRSM substitutes in the working precision after scaling B by alpha, as the netlib code does. */
+#define GEN_TR(T, SFX)                                                                                      \
+  static cx_##SFX tri_##SFX(const T *a, long lda, int uplo, int trans, int unit, int cplx, long i, long k) { \
+    /* E(i,k) = op(A)(i,k); zero outside the triangle */                                                    \
+    long r = (trans & 1) ? k : i, c = (trans & 1) ? i : k;                                                  \
+    cx_##SFX z = {0, 0};                                                                                    \
+    if (r == c) { if (unit) { z.re = 1; return z; } }                                                       \
+    else if (uplo ? (r < c) : (r > c)) return z;                                                            \
+    return cj_##SFX(ld_##SFX(a, r + c * lda, cplx), trans >= 2);                                            \
+  }                                                                                                         \
+  static void trxm_##SFX(int cplx, int solve, int side, int uplo, int trans, int unit, long m, long n,       \
+                         const T *alpha, const T *a, long lda, T *b, long ldb, double *gauge) {              \
+    cx_##SFX al = ld_##SFX(alpha, 0, cplx);                                                                 \
+    long ka = side ? n : m, nv = side ? m : n;     /* vector length, number of vectors */                   \
+    int eff_lower = (uplo != 0) != ((trans & 1) != 0);                                                      \
+    /* vector v: column v of B (left) or row v of B (right); right: x E = b  <=>  E^T x^T = b^T */          \
+    for (long v = 0; v < nv; v++) {                                                                         \
+      cx_##SFX x[ka > 0 ? ka : 1];                                                                          \
+      double g[ka > 0 ? ka : 1];                                                                            \
+      for (long i = 0; i < ka; i++) x[i] = ld_##SFX(b, side ? v + i * ldb : i + v * ldb, cplx);             \
+      int low = side ? !eff_lower : eff_lower;     /* triangle of the matrix that multiplies the vector */   \
+      if (!solve) {                                                                                         \
+        cx_##SFX y[ka > 0 ? ka : 1];                                                                        \
+        for (long i = 0; i < ka; i++) {                                                                     \
+          cx_##SFX acc = {0, 0};                                                                            \
+          double gg = 0;                                                                                    \
+          for (long k = low ? 0 : i; k < (low ? i + 1 : ka); k++) {                                         \
+            cx_##SFX e = side ? tri_##SFX(a, lda, uplo, trans, unit, cplx, k, i) : tri_##SFX(a, lda, uplo, trans, unit, cplx, i, k); \
+            acc = add_##SFX(acc, mul_##SFX(e, x[k]));                                                       \
+            gg += a1_##SFX(e) * a1_##SFX(x[k]);                                                             \
+          }                                                                                                 \
+          y[i] = mul_##SFX(al, acc);                                                                        \
+          g[i] = gg * a1_##SFX(al);                                                                         \
+        }                                                                                                   \
+        for (long i = 0; i < ka; i++) x[i] = y[i];                                                          \
+      } else {                                                                                              \
+        for (long i = 0; i < ka; i++) { x[i] = mul_##SFX(al, x[i]); g[i] = 0; }                             \
+        for (long ii = 0; ii < ka; ii++) {                                                                  \
+          long i = low ? ii : ka - 1 - ii;                                                                  \
+          cx_##SFX acc = x[i];                                                                              \
+          for (long k = low ? 0 : i + 1; k < (low ? i : ka); k++) {                                         \
+            cx_##SFX e = side ? tri_##SFX(a, lda, uplo, trans, unit, cplx, k, i) : tri_##SFX(a, lda, uplo, trans, unit, cplx, i, k); \
+            cx_##SFX pr = mul_##SFX(e, x[k]);                                                               \
+            acc.re -= pr.re; acc.im -= pr.im;                                                               \
+          }                                                                                                 \
+          if (!unit) {                                                                                      \
+            cx_##SFX d = tri_##SFX(a, lda, uplo, trans, 0, cplx, i, i);                                     \
+            T den = d.re * d.re + d.im * d.im;                                                              \
+            cx_##SFX q; q.re = (acc.re * d.re + acc.im * d.im) / den; q.im = (acc.im * d.re - acc.re * d.im) / den; \
+            if (!cplx) { q.re = acc.re / d.re; q.im = 0; }                                                  \
+            acc = q;                                                                                        \
+          }                                                                                                 \
+          x[i] = acc;                                                                                       \
+        }                                                                                                   \
+      }                                                                                                     \
+      for (long i = 0; i < ka; i++) {                                                                       \
+        st_##SFX(b, side ? v + i * ldb : i + v * ldb, cplx, x[i]);                                          \
+        if (gauge) gauge[side ? v + i * m : i + v * m] = g[i];                                              \
+      }                                                                                                     \
+    }                                                                                                       \
+  }
+GEN_TR(float, f)
+GEN_TR(double, d)
+
+
 /* C := alpha*A*B + beta*C (side 0) or alpha*B*A + beta*C (side 1); A symmetric (herm 0) or Hermitian
  * (herm 1), only its uplo triangle (0 upper, 1 lower) is read.  alpha/beta: 1 value, 2 for complex. */
 int oracle_symm(int dtype, int herm, int side, int uplo, long m, long n, const void *alpha, const void *a, long lda,
@@ -180,5 +247,76 @@ int oracle_check_rankk(int two, int uplo, int trans, long n, long k, long lda, l
   if (n < 0) info = 3;
   if (trans < 0) info = 2;
   if (uplo < 0) info = 1;
+  return info;
+}
+
+/* B := alpha*op(A)*B / alpha*B*op(A) (solve 0) or the solution X of op(A)*X = alpha*B / X*op(A) = alpha*B
+ * (solve 1), in place on b.  side 0 left, 1 right; uplo 0 upper, 1 lower; trans 0 N, 1 T, 2 conj, 3 conj-trans
+ * (real types: 2 = N, 3 = T); unit 1 = unit diagonal.  gauge (m x n, ld m) only meaningful for solve 0. */
+int oracle_trxm(int dtype, int solve, int side, int uplo, int trans, int unit, long m, long n, const void *alpha, const void *a,
+                long lda, void *b, long ldb, double *gauge) {
+  if (m <= 0 || n <= 0) return 0;
+  int cplx = dtype == OR_C || dtype == OR_Z;
+  if (!cplx) trans &= 1;
+  if (dtype == OR_S || dtype == OR_C)
+    trxm_f(cplx, solve, side, uplo, trans, unit, m, n, (const float *)alpha, (const float *)a, lda, (float *)b, ldb, gauge);
+  else if (dtype == OR_D || dtype == OR_Z)
+    trxm_d(cplx, solve, side, uplo, trans, unit, m, n, (const double *)alpha, (const double *)a, lda, (double *)b, ldb, gauge);
+  else return -1;
+  return 0;
+}
+
+/* The ctest check of a TRSM result (c_dblat3.f:1195-1235 multiplies the solution back with DMMCH):
+ * max over elements of |op(A)*X - alpha*B0| / (eps * (sum |op(A)||X| + |alpha*B0|)), evaluated in long
+ * double so the checker adds no rounding of its own.  A result passes ctest when this is below 16. */
+double oracle_trsm_residual(int dtype, int side, int uplo, int trans, int unit, long m, long n, const void *alpha, const void *a,
+                            long lda, const void *b0, long ldb0, const void *x, long ldx) {
+  int cplx = dtype == OR_C || dtype == OR_Z, dbl = dtype == OR_D || dtype == OR_Z;
+  if (!cplx) trans &= 1;
+  double eps = dbl ? ldexp(1.0, -52) : ldexp(1.0, -23), worst = 0;
+#define LD_RE(p, idx) (dbl ? (long double)((const double *)(p))[cplx ? 2 * (idx) : (idx)] : (long double)((const float *)(p))[cplx ? 2 * (idx) : (idx)])
+#define LD_IM(p, idx) (!cplx ? 0.0L : dbl ? (long double)((const double *)(p))[2 * (idx) + 1] : (long double)((const float *)(p))[2 * (idx) + 1])
+  long double are = LD_RE(alpha, 0), aim = LD_IM(alpha, 0);
+  long ka = side ? n : m;
+  for (long j = 0; j < n; j++)
+    for (long i = 0; i < m; i++) {
+      long double sre = 0, sim = 0, g = 0;
+      for (long l = 0; l < ka; l++) {
+        /* left: E(i,l) X(l,j); right: X(i,l) E(l,j) */
+        long ei = side ? l : i, ek = side ? j : l;
+        long r = (trans & 1) ? ek : ei, c = (trans & 1) ? ei : ek;
+        long double ere, eim;
+        if (r == c && unit) { ere = 1; eim = 0; }
+        else if (r != c && (uplo ? (r < c) : (r > c))) continue;
+        else { ere = LD_RE(a, r + c * lda); eim = LD_IM(a, r + c * lda); if (trans >= 2) eim = -eim; }
+        long xi = side ? i + l * ldx : l + j * ldx;
+        long double xre = LD_RE(x, xi), xim = LD_IM(x, xi);
+        sre += ere * xre - eim * xim; sim += ere * xim + eim * xre;
+        g += (fabsl(ere) + fabsl(eim)) * (fabsl(xre) + fabsl(xim));
+      }
+      long double bre = LD_RE(b0, i + j * ldb0), bim = LD_IM(b0, i + j * ldb0);
+      long double tre = are * bre - aim * bim, tim = are * bim + aim * bre;
+      long double err = fabsl(sre - tre) + fabsl(sim - tim);
+      g += fabsl(tre) + fabsl(tim);
+      double ratio = g > 0 ? (double)(err / (eps * g)) : (err > 0 ? 1e300 : 0.0);
+      if (ratio > worst) worst = ratio;
+    }
+#undef LD_RE
+#undef LD_IM
+  return worst;
+}
+
+/* interface/trsm.c:188-197 (side, uplo, trans, unit in their decoded form, -1 = illegal) */
+int oracle_check_trxm(int side, int uplo, int trans, int unit, long m, long n, long lda, long ldb, int ok) {
+  long nrowa = (side & 1) ? n : m;
+  int info = ok;
+  if (ldb < max1(m)) info = 11;
+  if (lda < max1(nrowa)) info = 9;
+  if (n < 0) info = 6;
+  if (m < 0) info = 5;
+  if (unit < 0) info = 4;
+  if (trans < 0) info = 3;
+  if (uplo < 0) info = 2;
+  if (side < 0) info = 1;
   return info;
 }

@@ -1,6 +1,6 @@
 /*
- * errexit_level3.c -- prints what xerbla_ receives for a table of illegal SYMM/HEMM, SYRK/HERK and
- * SYR2K/HER2K calls (CBLAS in both orders, Fortran), plus the quick returns.  No GPU needed: every
+ * errexit_level3.c -- prints what xerbla_ receives for a table of illegal SYMM/HEMM, SYRK/HERK,
+ * SYR2K/HER2K and TRMM/TRSM calls (CBLAS in both orders, Fortran), plus the quick returns.  No GPU needed: every
  * call must return before the library touches CUDA.  The SAME program is linked once against the
  * reference (oracle/_ref/generic/libopenblas_ref.so -> tests/golden/errexit_level3_reference.txt,
  * written by tests/golden/make_golden.py) and once against libopenblas_b200.so; the two outputs
@@ -39,6 +39,9 @@ static void show(const char *what) {
 #define BADS ((enum CBLAS_SIDE)0)
 #define BADU ((enum CBLAS_UPLO)0)
 #define BADT ((enum CBLAS_TRANSPOSE)0)
+#define NU CblasNonUnit
+#define UN CblasUnit
+#define BADD ((enum CBLAS_DIAG)0)
 
 int main(void) {
   double a[16] = {0}, b[16] = {0}, c[16];
@@ -98,6 +101,31 @@ int main(void) {
     cblas_zsyr2k(ord, LO, N_, 2, 0, zal, a, 2, b, 1, zbe, c, 2); show(W("zsyr2k ldb N"));
     cblas_cher2k(ord, LO, T_, 0, 0, cal, fa, 1, fb, 1, 1.f, fc, 1); show(W("cher2k trans T (illegal)"));
     cblas_zher2k(ord, U_, C_, 0, 2, zal, a, 1, b, 2, 1.0, c, 1); show(W("zher2k lda C"));
+    /* TRMM / TRSM: side, uplo, trans, diag, m, n, lda (left: vs m; right: vs n), ldb */
+    cblas_dtrmm(ord, BADS, U_, N_, NU, 0, 0, 1.0, a, 1, c, 1); show(W("dtrmm side"));
+    cblas_dtrmm(ord, L_, BADU, N_, NU, 0, 0, 1.0, a, 1, c, 1); show(W("dtrmm uplo"));
+    cblas_dtrmm(ord, L_, U_, BADT, NU, 0, 0, 1.0, a, 1, c, 1); show(W("dtrmm trans"));
+    cblas_dtrmm(ord, L_, U_, N_, BADD, 0, 0, 1.0, a, 1, c, 1); show(W("dtrmm diag"));
+    cblas_dtrmm(ord, L_, U_, N_, NU, -1, 0, 1.0, a, 1, c, 1); show(W("dtrmm m<0"));
+    cblas_dtrmm(ord, R_, LO, T_, UN, 0, -1, 1.0, a, 1, c, 1); show(W("dtrmm n<0"));
+    cblas_dtrmm(ord, L_, U_, N_, NU, 2, 0, 1.0, a, 1, c, 2); show(W("dtrmm lda left m=2"));
+    cblas_dtrmm(ord, R_, U_, N_, NU, 0, 2, 1.0, a, 1, c, 2); show(W("dtrmm lda right n=2"));
+    cblas_dtrmm(ord, L_, LO, C_, NU, 2, 0, 1.0, a, 2, c, 1); show(W("dtrmm ldb m=2"));
+    cblas_dtrmm(ord, R_, LO, C_, NU, 0, 2, 1.0, a, 2, c, 1); show(W("dtrmm ldb n=2"));
+    cblas_dtrmm(ord, BADS, U_, N_, NU, 2, 3, 1.0, a, 1, c, 1); show(W("dtrmm side + others"));
+    cblas_strmm(ord, L_, U_, N_, BADD, 0, 0, 1.f, fa, 1, fc, 1); show(W("strmm diag"));
+    cblas_ctrmm(ord, L_, U_, CblasConjNoTrans, NU, 2, 0, cal, fa, 1, fc, 2); show(W("ctrmm lda (R legal)"));
+    cblas_ztrmm(ord, R_, U_, C_, UN, 0, -1, zal, a, 1, c, 1); show(W("ztrmm n<0"));
+    cblas_dtrsm(ord, BADS, U_, N_, NU, 0, 0, 1.0, a, 1, c, 1); show(W("dtrsm side"));
+    cblas_dtrsm(ord, L_, U_, BADT, NU, 0, 0, 1.0, a, 1, c, 1); show(W("dtrsm trans"));
+    cblas_dtrsm(ord, L_, U_, N_, NU, 2, 0, 1.0, a, 1, c, 2); show(W("dtrsm lda left m=2"));
+    cblas_dtrsm(ord, R_, U_, N_, NU, 0, 2, 1.0, a, 1, c, 2); show(W("dtrsm lda right n=2"));
+    cblas_dtrsm(ord, L_, LO, T_, UN, 2, 0, 1.0, a, 2, c, 1); show(W("dtrsm ldb m=2"));
+    cblas_strsm(ord, L_, BADU, N_, NU, 0, 0, 1.f, fa, 1, fc, 1); show(W("strsm uplo"));
+    cblas_ctrsm(ord, R_, U_, N_, NU, -1, 0, cal, fa, 1, fc, 1); show(W("ctrsm m<0"));
+    cblas_ztrsm(ord, L_, U_, N_, BADD, 0, 0, zal, a, 1, c, 1); show(W("ztrsm diag"));
+    cblas_dtrsm(ord, L_, U_, N_, NU, 0, 3, 1.0, a, 1, c, 1); show(W("dtrsm m == 0"));
+    cblas_dtrmm(ord, R_, U_, N_, NU, 3, 0, 1.0, a, 1, c, 3); show(W("dtrmm n == 0"));
     /* quick returns */
     cblas_dsymm(ord, L_, U_, 0, 3, 1.0, a, 1, b, 1, 1.0, c, 1); show(W("dsymm m == 0"));
     cblas_dsymm(ord, R_, U_, 3, 0, 1.0, a, 1, b, 3, 1.0, c, 3); show(W("dsymm n == 0"));
@@ -127,6 +155,15 @@ int main(void) {
     zher2k_(&lo, &t, &z, &z, zal, a, &one, b, &one, &be, c, &one); show("f77 zher2k trans t (illegal)");
     cher2k_(&lo, &cc, &z, &m1, cal, fa, &one, fb, &one, &fbe, fc, &one); show("f77 cher2k k<0");
     dsyrk_(&u, &n, &z, &two, &al, a, &one, &be, c, &one); show("f77 dsyrk n == 0");
+    /* trsm.c:207 hands xerbla_ sizeof(ERROR_NAME)-1: the name arrives without its NUL */
+    dtrmm_(&x, &u, &n, &n, &z, &z, &al, a, &one, c, &one); show("f77 dtrmm side");
+    dtrmm_(&l, &u, &x, &n, &z, &z, &al, a, &one, c, &one); show("f77 dtrmm trans");
+    dtrmm_(&l, &u, &r, &u, &z, &z, &al, a, &one, c, &one); show("f77 dtrmm trans r (legal), diag u");
+    dtrmm_(&l, &u, &n, &x, &z, &z, &al, a, &one, c, &one); show("f77 dtrmm diag");
+    dtrsm_(&r, &lo, &cc, &n, &z, &two, &al, a, &one, c, &one); show("f77 dtrsm lda right");
+    dtrsm_(&l, &lo, &t, &u, &two, &z, &al, a, &two, c, &one); show("f77 dtrsm ldb");
+    ztrsm_(&l, &u, &n, &n, &m1, &z, zal, a, &one, c, &one); show("f77 ztrsm m<0");
+    ctrmm_(&l, &x, &n, &n, &z, &z, cal, fa, &one, fc, &one); show("f77 ctrmm uplo");
   }
   for (int i = 0; i < 16; i++)
     if (c[i] != 42.0 || fc[i] != 42.0f) { printf("C was written at %d\n", i); break; }

@@ -8,8 +8,7 @@ oracle/_ref has been built from it by oracle/build_ref.py).
                     ragged shapes, padded leading dimensions and the ctest alpha/beta values.
                     The oracle must reproduce these bit for bit; the GPU path within the bound.
   bf16_golden.npz   fp32 -> bf16 -> fp32 conversions by the reference's sbstobf16_/sbf16tos_.
-  ctest_in3/?in3    the reference's ctest input files (ctest/{s,d,c,z}in3) with TRMM and TRSM
-                    switched to F -- the data lines are untouched.
+  ctest_in3/?in3    the reference's ctest input files (ctest/{s,d,c,z}in3), every routine enabled.
 """
 import ctypes as C
 import os
@@ -96,7 +95,7 @@ def main():
         lines = open(os.path.join(REF, "ctest", f"{p}in3")).read().splitlines()
         res = []
         for ln in lines:
-            if ln.startswith("cblas_") and ln.split()[0][7:] in ("trmm", "trsm"):      # not implemented by the library
+            if False:      # every routine of the level-3 driver is implemented by the library: nothing is switched off
                 name, rest = ln.split(None, 1)
                 ln = f"{name:<12s} F" + rest[1:]
             res.append(ln)

@@ -1,13 +1,14 @@
 #!/usr/bin/env python3
-"""Writes tests/golden/level3_golden.npz and tests/golden/errexit_level3_reference.txt: fixtures
-produced by the REFERENCE itself for the symmetric level-3 family (SYMM/HEMM, SYRK/HERK,
-SYR2K/HER2K), run in the authoring container where /root/reference is mounted and oracle/_ref has
+"""Writes tests/golden/level3_golden.npz, trxm_golden.npz and errexit_level3_reference.txt: fixtures
+produced by the REFERENCE itself for the rest of level 3 (SYMM/HEMM, SYRK/HERK, SYR2K/HER2K,
+TRMM/TRSM), run in the authoring container where /root/reference is mounted and oracle/_ref has
 been built from it by oracle/build_ref.py (GENERIC target, one thread: deterministic).
 
   level3_golden.npz                 seeded inputs and the reference's outputs for every precision,
                                     routine, side / uplo / trans combination, ragged sizes, padded
                                     leading dimensions, the ctest alpha/beta values and the
                                     alpha == 0 / k == 0 / beta == 0 / beta == 1 corners
+  trxm_golden.npz                   the same for TRMM / TRSM: every side / uplo / trans / diag combination
   errexit_level3_reference.txt      what the reference's entry points hand to xerbla_ for the
                                     table of illegal calls in tests/c/errexit_level3.c
 """
@@ -92,6 +93,40 @@ def main():
     out["meta"] = np.array(meta, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "level3_golden.npz"), **out)
     print("level3_golden.npz:", len(meta), "cases")
+
+    # ---- TRMM / TRSM: every side / uplo / trans / diag combination; A's diagonal gets +1 like ctest's
+    # DMAKE (c_dblat3.f:2084-2087), its unreferenced triangle and a unit diagonal are set to NaN
+    rng = np.random.default_rng(20261019)
+    out, meta = {}, []
+    sizes = [(1, 1), (2, 3), (7, 5), (9, 19), (19, 9), (13, 11), (17, 18)]
+    i = 0
+    for dtype in (cpu.S, cpu.D, cpu.CX, cpu.Z):
+        cplx = dtype in (cpu.CX, cpu.Z)
+        for solve in (0, 1):
+            for side in (0, 1):
+                for uplo in (0, 1):
+                    for trans in range(4 if cplx else 2):
+                        for unit in (0, 1):
+                            m, n = sizes[i % len(sizes)]
+                            alpha = [(0.7 - 0.9j) if cplx else 0.7, 1.0, 0.0][i % 7 // 3 if i % 7 >= 5 else 0]
+                            i += 1
+                            ka = n if side else m
+                            lda, ldb = ka + 2, m + 3
+                            a, b0 = operand(rng, dtype, ka, lda), operand(rng, dtype, n, ldb)
+                            a[np.arange(ka), np.arange(ka)] += 1.0
+                            jj, ii = np.meshgrid(np.arange(ka), np.arange(lda), indexing="ij")
+                            a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
+                            if unit:
+                                a[np.arange(ka), np.arange(ka)] = np.nan
+                            b0[:, m:] = -1e10
+                            b = b0.copy()
+                            cpu.call_trxm(ref.lib, dtype, solve, side, uplo, trans, unit, m, n, alpha, a, lda, b, ldb)
+                            idx = len(meta)
+                            out[f"a{idx}"], out[f"b0_{idx}"], out[f"b{idx}"] = a, b0, b
+                            meta.append([dtype, solve, side, uplo, trans, unit, m, n, lda, ldb, complex(alpha).real, complex(alpha).imag])
+    out["meta"] = np.array(meta, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "trxm_golden.npz"), **out)
+    print("trxm_golden.npz:", len(meta), "cases")
 
     refdir = os.path.dirname(cpu.ref_path("generic"))
     with tempfile.TemporaryDirectory() as tmp:

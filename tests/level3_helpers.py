@@ -62,3 +62,53 @@ def bind(lib):
     def call(which, *args):
         return (cpu.call_symm if which == "symm" else cpu.call_rankk)(lib, *args)
     return call
+
+
+# ---- TRMM / TRSM ---------------------------------------------------------------------------
+TRSM_THRESH = 16.0      # ctest's THRESH on err / (eps * gauge) of the multiplied-back solution
+
+
+def tri_operand(rng, dtype, ka, lda, uplo, unit):
+    """Triangular test matrix as ctest's DMAKE builds it (c_dblat3.f:2084-2087: diagonal + 1); the
+    triangle that must not be referenced, and a unit diagonal, are NaN."""
+    a = operand(rng, dtype, ka, lda)
+    a[np.arange(ka), np.arange(ka)] += 1.0
+    jj, ii = np.meshgrid(np.arange(ka), np.arange(lda), indexing="ij")
+    a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
+    if unit:
+        a[np.arange(ka), np.arange(ka)] = np.nan
+    return a
+
+
+def check_trxm(oracle, lib, case, a, b0, ref_b=None):
+    """case = (dtype, solve, side, uplo, trans, unit, m, n, lda, ldb, alpha).  Runs `lib` (or takes
+    ref_b as its result), checks padding rows, and the product bound (TRMM) or ctest's residual ratio
+    (TRSM).  Returns the ratio."""
+    dtype, solve, side, uplo, trans, unit, m, n, lda, ldb, alpha = case
+    if ref_b is None:
+        got = b0.copy()
+        cpu.call_trxm(lib, dtype, solve, side, uplo, trans, unit, m, n, alpha, a, lda, got, ldb)
+    else:
+        got = ref_b
+    assert np.array_equal(got[:, m:].view(np.uint8), b0[:, m:].view(np.uint8)), ("padding rows changed",) + tuple(case[:8])
+    assert not np.isnan(got[:, :m]).any(), ("NaN leaked from the unreferenced part of A",) + tuple(case[:8])
+    if complex(alpha) == 0:
+        assert np.all(got[:, :m] == 0), case[:8]
+        return 0.0
+    if solve:
+        ratio = oracle.trsm_residual(dtype, side, uplo, trans, unit, m, n, alpha, a, lda, b0, ldb, got, ldb)
+        assert ratio < TRSM_THRESH, ("ctest residual ratio", ratio) + tuple(case[:8])
+        return ratio
+    want = b0.copy()
+    g = oracle.trxm(dtype, 0, side, uplo, trans, unit, m, n, alpha, a, lda, want, ldb)
+    K = (n if side else m) + 1
+    err = np.abs(got[:, :m].astype(np.complex128) - want[:, :m].astype(np.complex128))
+    bound = C_BOUND * K * EPS[dtype] * g[:n, :m]
+    assert np.all(err <= bound + 1e-300), ("componentwise bound", float((err / np.maximum(bound, 1e-300)).max())) + tuple(case[:8])
+    return float((err / np.maximum(bound, 1e-300)).max())
+
+
+def trxm_meta_case(row):
+    dtype, solve, side, uplo, trans, unit, m, n, lda, ldb = (int(v) for v in row[:10])
+    alpha = complex(row[10], row[11]) if dtype in (cpu.CX, cpu.Z) else float(row[10])
+    return (dtype, solve, side, uplo, trans, unit, m, n, lda, ldb, alpha)

@@ -75,8 +75,8 @@ def test_error_exits_and_quick_returns_through_c_abi(tmp_path, ob):
 
 def test_level3_error_exits_match_the_reference_line_for_line(tmp_path, ob):
     """tests/c/errexit_level3.c against libopenblas_b200.so must print exactly what it printed against
-    the reference (tests/golden/errexit_level3_reference.txt): 157 probes of SYMM/HEMM, SYRK/HERK,
-    SYR2K/HER2K over column-major, row-major, an illegal order and the Fortran ABI, plus quick returns.
+    the reference (tests/golden/errexit_level3_reference.txt): 237 probes of SYMM/HEMM, SYRK/HERK,
+    SYR2K/HER2K, TRMM/TRSM over column-major, row-major, an illegal order and the Fortran ABI, plus quick returns.
     No CUDA call is made (legal probes are no-ops: beta == 1 with k == 0 or an empty matrix)."""
     exe = tmp_path / "errexit_level3"
     subprocess.check_call(["gcc", "-O1", "-Wall", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", "errexit_level3.c"),
@@ -84,7 +84,7 @@ def test_level3_error_exits_match_the_reference_line_for_line(tmp_path, ob):
     r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout
     want = open(os.path.join(ROOT, "tests", "golden", "errexit_level3_reference.txt")).read()
-    assert len(want.splitlines()) == 157
+    assert len(want.splitlines()) == 237
     assert r.stdout == want
 
 

@@ -1,9 +1,9 @@
 """The reference's own acceptance programs, UNMODIFIED, linked against libopenblas_b200.so as a
 drop-in (oracle/build_ref.py compiles ctest/c_?blat3c.c, c_?blas3.c, c_?3chke.c, c_xerbla.c from
 /root/reference and links them first against our library): 27 783 cblas_?gemm calls per layout
-for s/d/z (17 496 for c), the SYMM/HEMM, SYRK/HERK and SYR2K/HER2K sweeps, and the error-exit
+for s/d/z (17 496 for c), the SYMM/HEMM, SYRK/HERK, SYR2K/HER2K, TRMM and TRSM sweeps, and the error-exit
 checks of all of them, each judged by the reference's own checkers (DMMCH and friends).
-Inputs: the reference's ?in3 files with TRMM and TRSM switched off
+Inputs: the reference's ?in3 files, every routine enabled
 (tests/golden/ctest_in3, written by tests/golden/make_golden.py)."""
 import os
 import subprocess
@@ -31,7 +31,7 @@ def test_ctest_level3_gemm(p):
     calls = 17496 if p == "c" else 27783
     assert re.search(rf"cblas_{p}gemm\s+PASSED THE COLUMN-MAJOR COMPUTATIONAL TESTS \(\s*{calls} CALLS\)", out), out[-2000:]
     assert re.search(rf"cblas_{p}gemm\s+PASSED THE ROW-MAJOR\s+COMPUTATIONAL TESTS \(\s*{calls} CALLS\)", out), out[-2000:]
-    family = ["symm", "syrk", "syr2k"] + (["hemm", "herk", "her2k"] if p in "cz" else [])
+    family = ["symm", "syrk", "syr2k", "trmm", "trsm"] + (["hemm", "herk", "her2k"] if p in "cz" else [])
     for r in family:
         assert len(re.findall(rf"cblas_{p}{r}\s+PASSED THE TESTS OF ERROR-EXITS", out)) == 1, (r, out[-3000:])
         assert re.search(rf"cblas_{p}{r}\s+PASSED THE COLUMN-MAJOR COMPUTATIONAL TESTS \(\s*\d+ CALLS\)", out), (r, out[-3000:])

@@ -139,3 +139,57 @@ def test_level3_cblas_row_major_and_device_pointers(ob, oracle):
     assert np.allclose(got[low], want[low], rtol=0, atol=1e-11)
     assert np.array_equal(got[~low], c_before.cpu().numpy().T[~low])
     assert "dgemm_dmma" in ob.cblas.last_kernel() or "tri_merge" in ob.cblas.last_kernel()
+
+
+def test_trxm_golden_vectors(ob, oracle):
+    """All 192 reference-generated TRMM / TRSM cases (every side / uplo / trans / diag combination)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trxm_golden.npz"))
+    worst = 0.0
+    for idx, row in enumerate(g["meta"]):
+        case = L.trxm_meta_case(row)
+        worst = max(worst, L.check_trxm(oracle, ob.lib(), case, g[f"a{idx}"], g[f"b0_{idx}"]))
+    assert worst < L.TRSM_THRESH
+
+
+@pytest.mark.parametrize("dtype", [cpu.S, cpu.D, cpu.CX, cpu.Z])
+def test_trxm_recursive_sizes(ob, oracle, dtype):
+    """Triangles of 150 and 203 rows: three / four levels of the recursive split, ragged 64-blocks at
+    the end, the coupling GEMMs on the fast kernels; every side / uplo / trans / diag combination."""
+    rng = np.random.default_rng(900 + dtype)
+    cplx = dtype in (cpu.CX, cpu.Z)
+    alpha = (0.7 - 0.9j) if cplx else 0.7
+    for solve in (0, 1):
+        for side in (0, 1):
+            for uplo in (0, 1):
+                for trans in range(4 if cplx else 2):
+                    for unit in (0, 1):
+                        m, n = (150, 90) if (trans + unit) % 2 == 0 else (70, 203)
+                        ka = n if side else m
+                        a = L.tri_operand(rng, dtype, ka, ka + 1, uplo, unit)
+                        if solve:      # keep the triangular system well conditioned at this size: scale the off-diagonal part
+                            off = ~np.eye(ka, ka + 1, dtype=bool)
+                            a[off] *= 4.0 / ka
+                        b0 = L.operand(rng, dtype, n, m + 2)
+                        case = (dtype, solve, side, uplo, trans, unit, m, n, ka + 1, m + 2, alpha)
+                        L.check_trxm(oracle, ob.lib(), case, a, b0)
+
+
+def test_trsm_device_pointers_large(ob):
+    """DTRSM on device-resident operands, 2048 x 1024, left lower: residual against a float64 product."""
+    import ctypes as C
+    import torch
+    lib = ob.lib()
+    m, n = 2048, 1024
+    a = torch.rand((m, m), dtype=torch.float64, device="cuda") - 0.5          # column-major view: a[j, i] = A(i, j)
+    a = a * (4.0 / m) + torch.eye(m, dtype=torch.float64, device="cuda") * 1.5
+    b = torch.rand((n, m), dtype=torch.float64, device="cuda") - 0.5
+    b0 = b.clone()
+    one = lambda v: C.byref(C.c_int(v))
+    al = C.c_double(0.7)
+    lib.dtrsm_(C.c_char_p(b"L"), C.c_char_p(b"L"), C.c_char_p(b"N"), C.c_char_p(b"N"), one(m), one(n), C.byref(al),
+               C.c_void_p(a.data_ptr()), one(m), C.c_void_p(b.data_ptr()), one(m))
+    torch.cuda.synchronize()
+    A = torch.tril(a.T)                                                       # A(i, j), lower
+    X = b.T
+    res = (A @ X - 0.7 * b0.T).abs().max().item()
+    assert res < 1e-12, res

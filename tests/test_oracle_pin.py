@@ -252,3 +252,42 @@ def test_level3_argument_checks_match_reference_error_exits(oracle):
     assert oracle.check_rankk(1, 0, 1, 0, 2, 2, 1, 1, -1) == want["dsyr2k ldb T"] == 9
     assert oracle.check_rankk(1, 1, 0, 2, 0, 2, 2, 1, -1) == want["dsyr2k ldc"] == 12
     assert oracle.check_rankk(1, 0, 0, 2, 0, 1, 2, 2, -1) == want["dsyr2k lda"] == 7
+
+
+def test_trxm_oracle_and_checker_accept_reference_golden(oracle):
+    """tests/golden/trxm_golden.npz: the reference's TRMM results must sit within the bound of the
+    oracle's, and its TRSM solutions must pass the oracle's restatement of ctest's residual check
+    (the check is what pins TRSM: forward errors depend on conditioning, residuals do not)."""
+    import level3_helpers as L
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trxm_golden.npz"))
+    assert len(g["meta"]) == 192
+    worst_mm = worst_sm = 0.0
+    for idx, row in enumerate(g["meta"]):
+        case = L.trxm_meta_case(row)
+        r = L.check_trxm(oracle, None, case, g[f"a{idx}"], g[f"b0_{idx}"], ref_b=g[f"b{idx}"])
+        if case[1]:
+            worst_sm = max(worst_sm, r)
+            # and the oracle's own substitution passes the same check
+            mine = g[f"b0_{idx}"].copy()
+            oracle.trxm(case[0], 1, case[2], case[3], case[4], case[5], case[6], case[7], case[10], g[f"a{idx}"], case[8], mine, case[9])
+            L.check_trxm(oracle, None, case, g[f"a{idx}"], g[f"b0_{idx}"], ref_b=mine)
+        else:
+            worst_mm = max(worst_mm, r)
+    assert worst_mm < 1.0 and worst_sm < L.TRSM_THRESH
+
+
+def test_trxm_argument_checks_match_reference_error_exits(oracle):
+    want = {}
+    for ln in open(os.path.join(ROOT, "tests", "golden", "errexit_level3_reference.txt")):
+        if ln.startswith("col ") and "info=" in ln:
+            want[ln[4:34].strip()] = int(ln.rsplit("info=", 1)[1])
+    assert oracle.check_trxm(-1, 0, 0, 0, 0, 0, 1, 1, -1) == want["dtrmm side"] == 1
+    assert oracle.check_trxm(0, -1, 0, 0, 0, 0, 1, 1, -1) == want["dtrmm uplo"] == 2
+    assert oracle.check_trxm(0, 0, -1, 0, 0, 0, 1, 1, -1) == want["dtrmm trans"] == 3
+    assert oracle.check_trxm(0, 0, 0, -1, 0, 0, 1, 1, -1) == want["dtrmm diag"] == 4
+    assert oracle.check_trxm(0, 0, 0, 0, -1, 0, 1, 1, -1) == want["dtrmm m<0"] == 5
+    assert oracle.check_trxm(1, 1, 1, 1, 0, -1, 1, 1, -1) == want["dtrmm n<0"] == 6
+    assert oracle.check_trxm(0, 0, 0, 0, 2, 0, 1, 2, -1) == want["dtrmm lda left m=2"] == 9
+    assert oracle.check_trxm(1, 0, 0, 0, 0, 2, 1, 2, -1) == want["dtrmm lda right n=2"] == 9
+    assert oracle.check_trxm(0, 1, 3, 0, 2, 0, 2, 1, -1) == want["dtrmm ldb m=2"] == 11
+    assert oracle.check_trxm(-1, 0, 0, 0, 2, 3, 1, 1, -1) == want["dtrmm side + others"] == 1
