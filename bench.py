@@ -419,7 +419,7 @@ def run_sweep(args):
 
 def run_sweep_level3(args):
     """Developer view: the symmetric level-3 family on device-resident operands, TFLOP/s with the
-    conventional flop counts (SYMM 2*m*m*n, SYRK n*n*k, SYR2K 2*n*n*k real; complex x4) -- what a GEMM
+    conventional flop counts (SYMM 2*m*m*n, SYRK n*n*k, SYR2K 2*n*n*k, TRMM/TRSM m*m*n real; complex x4) -- what a GEMM
     of the same useful work would be credited with."""
     import ctypes as C
     import torch
@@ -438,12 +438,16 @@ def run_sweep_level3(args):
             n = k = nsz
             mk = lambda: (torch.rand((nsz, nsz, 2) if cplx else (nsz, nsz), device=dev, dtype=rdt) - 0.5)
             a, b, c = mk(), mk(), mk()
+            a.mul_(1.0 / nsz)                                     # keeps the unit-diagonal TRSM sweeps bounded
             al2, be2 = (ct * 2)(0.7, 0.2), (ct * 2)(1.3, 0.1)
             alr, ber = ct(0.7), ct(1.3)
             pa, pb, pc = C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr())
             jobs = [("symm", lambda: getattr(lib, dtype + "symm_")(C.c_char_p(b"L"), C.c_char_p(b"U"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
                     ("syrk", lambda: getattr(lib, dtype + "syrk_")(C.c_char_p(b"L"), C.c_char_p(b"N"), i_(n), i_(k), al2, pa, i_(n), be2, pc, i_(n)), 1.0),
                     ("syr2k", lambda: getattr(lib, dtype + "syr2k_")(C.c_char_p(b"U"), C.c_char_p(b"T"), i_(n), i_(k), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0)]
+            jobs += [("trmm", lambda: getattr(lib, dtype + "trmm_")(C.c_char_p(b"L"), C.c_char_p(b"L"), C.c_char_p(b"N"), C.c_char_p(b"N"), i_(n), i_(n), al2, pa, i_(n), pc, i_(n)), 1.0),
+                     ("trsm", lambda: getattr(lib, dtype + "trsm_")(C.c_char_p(b"L"), C.c_char_p(b"L"), C.c_char_p(b"N"), C.c_char_p(b"U"), i_(n), i_(n), al2, pa, i_(n), pc, i_(n)), 1.0),
+                     ("trsm_right_upper_T", lambda: getattr(lib, dtype + "trsm_")(C.c_char_p(b"R"), C.c_char_p(b"U"), C.c_char_p(b"T"), C.c_char_p(b"U"), i_(n), i_(n), al2, pa, i_(n), pc, i_(n)), 1.0)]
             if cplx:
                 jobs += [("hemm", lambda: getattr(lib, dtype + "hemm_")(C.c_char_p(b"R"), C.c_char_p(b"L"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
                          ("herk", lambda: getattr(lib, dtype + "herk_")(C.c_char_p(b"U"), C.c_char_p(b"C"), i_(n), i_(k), C.byref(alr), pa, i_(n), C.byref(ber), pc, i_(n)), 1.0)]
