@@ -1,6 +1,6 @@
 /*
- * level3_oracle.c -- TEST INFRASTRUCTURE.  CPU restatement of the symmetric level-3 family
- * (SYMM/HEMM, SYRK/HERK, SYR2K/HER2K) used to check the CUDA path; never linked into the product.
+ * level3_oracle.c -- TEST INFRASTRUCTURE.  CPU restatement of the rest of level 3 (SYMM/HEMM,
+ * SYRK/HERK, SYR2K/HER2K, TRMM/TRSM) used to check the CUDA path; never linked into the product.
  *
  * It follows the SEMANTICS the reference implements -- the netlib definitions the reference
  * ships under reference/ and its ctest drivers check against:
