@@ -73,14 +73,16 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
   const float sgn_b = (g.transb & 2) ? -1.f : 1.f;    /* conj(B) */
 
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
-  const int64_t tiles = tiles_m * tiles_n;
+  const int64_t tiles = g.tri ? tri_tile_count(tiles_m) : tiles_m * tiles_n;      /* tri: m == n, square tiles */
   const int64_t ktiles = (g.k + BK - 1) / BK;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(csmem);
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
-    banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+    if (g.tri) tri_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
+    if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* uniform over the CTA: no barrier is skipped by part of it */
+    const bool masked = tri_partial(g.tri, m0, BM, n0, BN);
 
     u64 accp[4][4], accq[4][4];   /* [row i][col j]: P = sum a*br, Q = sum a*bi (see header) */
 #pragma unroll
@@ -177,7 +179,7 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
           out[e].y = alr * xi + ali * xr;
         }
         float2 *p = C + m + n * g.ldc;
-        if (vec_c && m + 1 < g.m) {
+        if (vec_c && m + 1 < g.m && !masked) {
           if (use_beta) {
             float4 old = *reinterpret_cast<const float4 *>(p);
             out[0].x += ber * old.x - bei * old.y; out[0].y += ber * old.y + bei * old.x;
@@ -188,6 +190,7 @@ cgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c) {
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             if (m + e >= g.m) break;
+            if (!tri_keep(g.tri, m + e, n)) continue;
             if (use_beta) {
               float2 old = p[e];
               out[e].x += ber * old.x - bei * old.y; out[e].y += ber * old.y + bei * old.x;
@@ -210,6 +213,7 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
     configured = true;
   }
   int64_t tiles = ((g.m + BM - 1) / BM) * ((g.n + BN - 1) / BN);
+  if (g.tri) tiles = tri_tile_count((g.m + BM - 1) / BM);
   int64_t cap = (int64_t)sm_count() * 2;
   int grid = (int)(tiles < cap ? tiles : cap);
   kern<<<grid, THREADS, SMEM_BYTES, stream>>>(g, vec_a, vec_b, vec_c);
@@ -221,6 +225,7 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
 cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   if (g.dtype != B200_C) return cudaErrorNotSupported;
   if (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 7) return cudaErrorNotSupported;
+  if (g.tri && g.m != g.n) return cudaErrorNotSupported;
   const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
   const int vec_a = (((uintptr_t)g.a & 15) == 0) && (g.lda % 2 == 0);
   const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 2 == 0);

@@ -258,7 +258,8 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
   const double *__restrict__ B = (const double *)g.b;
   double *__restrict__ C = (double *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
+  const int64_t tiles = g.tri ? tri_tile_count(tiles_m) : tiles_m * tiles_n;      /* tri: m == n, square tiles */
   const int64_t ktiles = (g.k + BK - 1) / BK;
 
   if (tid == 0) {
@@ -273,8 +274,9 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
     int slot = 0; uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       int64_t bm, bn;
-      banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+      if (g.tri) tri_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
       const int64_t m0 = bm * BM, n0 = bn * BN;
+      if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* consumers skip the same tiles */
       for (int64_t kt = 0; kt < ktiles; kt++) {
         const int64_t k0 = kt * BK;
         mbar_wait(empty_bar(slot), phase ^ 1);
@@ -308,8 +310,10 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
   int slot = 0; uint32_t phase = 0;
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
-    banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+    if (g.tri) tri_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
+    if (tri_outside(g.tri, m0, BM, n0, BN)) continue;
+    const bool masked = tri_partial(g.tri, m0, BM, n0, BN);
 
     double acc[FM][FN][2];
 #pragma unroll
@@ -349,16 +353,18 @@ dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
         if (m >= g.m) continue;
         double *p = C + m + n * g.ldc;
         double r0 = alpha * acc[i][j][0], r1 = alpha * acc[i][j][1];
-        if (vec_c && m + 1 < g.m) {
+        if (vec_c && m + 1 < g.m && !masked) {
           if (use_beta) {
             double2 old = *reinterpret_cast<const double2 *>(p);
             r0 = fma(beta, old.x, r0); r1 = fma(beta, old.y, r1);
           }
           *reinterpret_cast<double2 *>(p) = make_double2(r0, r1);
         } else {
-          if (use_beta) r0 = fma(beta, p[0], r0);
-          p[0] = r0;
-          if (m + 1 < g.m) {
+          if (tri_keep(g.tri, m, n)) {
+            if (use_beta) r0 = fma(beta, p[0], r0);
+            p[0] = r0;
+          }
+          if (m + 1 < g.m && tri_keep(g.tri, m + 1, n)) {
             if (use_beta) r1 = fma(beta, p[1], r1);
             p[1] = r1;
           }
@@ -380,6 +386,7 @@ cudaError_t launch_bulk_variant(const DeviceGemm &g, cudaStream_t stream) {
     configured = true;
   }
   int64_t tiles = ((g.m + C_::BM - 1) / C_::BM) * ((g.n + C_::BN - 1) / C_::BN);
+  if (g.tri) tiles = tri_tile_count((g.m + C_::BM - 1) / C_::BM);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
   static int probe = -1;   /* B200_DGEMM_PROBE_NOLOAD=1: timing probe only, results are garbage */
@@ -419,6 +426,7 @@ cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   if (cfg < 0) { const char *e = getenv("B200_DGEMM_CFG"); cfg = e ? atoi(e) : 5; }
   cudaError_t e;
   const char *name;
+  if (g.tri && (g.m != g.n || !(cfg >= 5 && bulk_eligible<CfgWide32>(g)))) return cudaErrorNotSupported;   /* only the producer-warp kernels mask */
   if (cfg >= 5 && bulk_eligible<CfgWide32>(g)) {
     /* Tile choice.  A 128x128 tile costs four 64x64 tiles; the grid runs in waves of one tile per SM.
      * When the 128x128 tiling leaves SMs idle (few tiles, or a mostly empty last wave) the 64x64
@@ -427,7 +435,8 @@ cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
     const char *t = getenv("B200_DGEMM_TILE");
     const int forced = t ? atoi(t) : 0;
     const int64_t sms = sm_count();
-    const int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+    int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+    if (g.tri) { t128 = (t128 + 1) / 2; t64 = (t64 + 1) / 2; }      /* about half the tiles are skipped */
     const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = 1.08 * (double)((t64 + sms - 1) / sms);
     const bool small_tile = forced == 64 || (forced != 128 && est64 < est128);
     if (small_tile) {

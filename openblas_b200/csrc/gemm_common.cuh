@@ -22,7 +22,34 @@ struct DeviceGemm {
   void *c;
   double alpha_re, alpha_im;
   double beta_re, beta_im;
+  /* 0: all of C.  1 / 2: only the lower / upper triangle of the (square) m x n window is computed
+   * and written (SYRK family, runtime_level3.inl): kernels that support it skip the tiles outside
+   * the triangle and mask the stores of the tiles the diagonal crosses; the others answer
+   * cudaErrorNotSupported and the caller falls back to block columns. */
+  int tri = 0;
 };
+
+/* triangle tests on a tile [m0, m0 + bm) x [n0, n0 + bn) and on an element */
+__host__ __device__ __forceinline__ bool tri_outside(int tri, int64_t m0, int bm, int64_t n0, int bn) {
+  return tri == 1 ? (m0 + bm - 1 < n0) : tri == 2 ? (m0 > n0 + bn - 1) : false;
+}
+__host__ __device__ __forceinline__ bool tri_partial(int tri, int64_t m0, int bm, int64_t n0, int bn) {
+  return tri == 1 ? (m0 < n0 + bn - 1) : tri == 2 ? (m0 + bm - 1 > n0) : false;
+}
+/* Kernels with SQUARE tiles enumerate only the nt*(nt+1)/2 tiles of the triangle (row by row of the
+ * lower triangle, mirrored for the upper one), so the static round-robin over persistent CTAs stays
+ * balanced; kernels with rectangular tiles walk all tiles and skip with tri_outside(). */
+__host__ __device__ __forceinline__ int64_t tri_tile_count(int64_t nt) { return nt * (nt + 1) / 2; }
+__device__ __forceinline__ void tri_tile_coords(int64_t u, int tri, int64_t &bm, int64_t &bn) {
+  int64_t r = (int64_t)((sqrt(8.0 * (double)u + 1.0) - 1.0) * 0.5);
+  while (r * (r + 1) / 2 > u) r--;
+  while ((r + 1) * (r + 2) / 2 <= u) r++;
+  const int64_t c = u - r * (r + 1) / 2;
+  if (tri == 1) { bm = r; bn = c; } else { bm = c; bn = r; }
+}
+__host__ __device__ __forceinline__ bool tri_keep(int tri, int64_t m, int64_t n) {
+  return tri == 1 ? m >= n : tri == 2 ? m <= n : true;
+}
 
 /* per-precision element traits */
 template <int DT> struct Traits;
@@ -67,6 +94,7 @@ cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, co
 cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const void *t, int64_t ldt, double beta_re,
                              double beta_im, void *c, int64_t ldc, cudaStream_t stream);
 
+cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cudaStream_t stream);
 /* base case of the recursive TRMM / TRSM: one nb x nb (nb <= 64) triangular block against nrhs vectors */
 cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,
                              int64_t fs_k, double ar, double ai, void *b, int64_t rs, int64_t cs, cudaStream_t stream);

@@ -247,6 +247,23 @@ cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff
   return e;
 }
 
+template <class T>
+__global__ void real_diagonal_kernel(int64_t n, T *__restrict__ c, int64_t ldc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c[i + i * ldc] = real_only(c[i + i * ldc]);
+}
+
+/* HERK / HER2K: the diagonal of the result is real by definition (zherkf.f:284, 321) */
+cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cudaStream_t stream) {
+  if (n <= 0 || (dtype != B200_C && dtype != B200_Z)) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  if (dtype == B200_C) real_diagonal_kernel<float2><<<blocks, 256, 0, stream>>>(n, (float2 *)c, ldc);
+  else real_diagonal_kernel<double2><<<blocks, 256, 0, stream>>>(n, (double2 *)c, ldc);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch("real_diagonal");
+  return e;
+}
+
 cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const void *t, int64_t ldt, double beta_re,
                              double beta_im, void *c, int64_t ldc, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;

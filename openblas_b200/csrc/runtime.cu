@@ -189,6 +189,7 @@ static cudaError_t dispatch(const DeviceGemm &g, cudaStream_t stream) {
     if (e != cudaErrorNotSupported) return e;
     if (forced == B200_K_FAST) return e; /* caller insisted: report "not supported" */
   }
+  if (g.tri) return cudaErrorNotSupported;   /* the generic kernel has no triangle mask: the caller uses block columns */
   return launch_generic(g, stream);
 }
 

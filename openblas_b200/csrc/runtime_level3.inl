@@ -19,9 +19,10 @@
 
 static cudaError_t gemm_on_device(int dtype, int ta, int tb, int64_t m, int64_t n, int64_t k, double ar, double ai,
                                   const void *a, int64_t lda, const void *b, int64_t ldb, double br, double bi, void *c,
-                                  int64_t ldc, cudaStream_t s) {
+                                  int64_t ldc, cudaStream_t s, int tri = 0) {
   if (m <= 0 || n <= 0) return cudaSuccess;
   DeviceGemm g;
+  g.tri = tri;
   g.dtype = dtype; g.transa = ta; g.transb = tb; g.m = m; g.n = n; g.k = k;
   g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a = a; g.b = b; g.c = c;
   g.alpha_re = ar; g.alpha_im = ai; g.beta_re = br; g.beta_im = bi;
@@ -136,6 +137,25 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
   const int op_second = p->trans ? B200_N : (herm ? B200_C_ : B200_T);
   auto at = [&](const char *x, int64_t ldx, int64_t i0) { return x + (p->trans ? (size_t)i0 * (size_t)ldx : (size_t)i0) * es; };
   const double ai2 = herm ? -ai : ai;  /* HER2K: the second product carries conj(alpha) */
+
+  /* Preferred: ONE launch per product with the triangle handled inside the GEMM kernel (tiles
+   * outside the triangle skipped, stores of the diagonal tiles masked): no small diagonal-block
+   * GEMMs, no scratch, the whole triangle's tiles share the SMs.  Kernels that cannot mask (generic
+   * kernel for tiny problems, cp.async variants for unaligned operands) answer "not supported"
+   * BEFORE launching anything, and the block-column scheme below takes over. */
+  const char *tri_env = getenv("B200_RANKK_TRI");          /* =0 forces the block-column scheme (tests cover both) */
+  const bool tri_gemm_ok = !(tri_env && atoi(tri_env) == 0);
+  if (tri_gemm_ok) {
+    const int tri = p->uplo ? 1 : 2;
+    cudaError_t e = gemm_on_device(p->dtype, op_first, op_second, n, n, k, ar, ai, a, lda, two ? b : a, two ? ldb : lda, br, bi, c, ldc, s, tri);
+    if (e == cudaSuccess) {
+      if (two) CK(gemm_on_device(p->dtype, op_first, op_second, n, n, k, ar, ai2, b, ldb, a, lda, 1.0, 0.0, c, ldc, s, tri));
+      if (herm) CK(launch_real_diagonal(p->dtype, n, c, ldc, s));
+      return 0;
+    }
+    if (e != cudaErrorNotSupported) return set_error(e, "triangular GEMM");
+  }
+
   const int64_t nb = rankk_block(n);
   const int64_t ldt = (int64_t)(round_up((size_t)nb * es, 128) / es);
   for (int64_t j0 = 0; j0 < n; j0 += nb) {

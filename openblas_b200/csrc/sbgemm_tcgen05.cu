@@ -587,7 +587,7 @@ cudaError_t launch_2cta_variant(const DeviceGemm &g, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t stream) {
-  if (g.dtype != B200_SB) return cudaErrorNotSupported;
+  if (g.dtype != B200_SB || g.tri) return cudaErrorNotSupported;
   /* TMA: 16-byte aligned bases, row pitch a multiple of 16 bytes; int32 tile arithmetic */
   if (((uintptr_t)g.a | (uintptr_t)g.b) & 15) return cudaErrorNotSupported;
   if ((g.lda % 8) || (g.ldb % 8) || ((uintptr_t)g.c & 3)) return cudaErrorNotSupported;

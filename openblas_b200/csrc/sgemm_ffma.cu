@@ -91,7 +91,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c, int probe) {
   const int tn = (warp / SC<TILE>::WARPS_M) * 4 + pn;
 
   const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
-  const int64_t tiles = tiles_m * tiles_n;
+  const int64_t tiles = g.tri ? tri_tile_count(tiles_m) : tiles_m * tiles_n;      /* tri: m == n, square tiles */
   const int64_t ktiles = (g.k + BK - 1) / BK;
   const float alpha = (float)g.alpha_re, beta = (float)g.beta_re;
   const bool use_beta = beta != 0.f;
@@ -102,8 +102,10 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c, int probe) {
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
-    banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+    if (g.tri) tri_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
+    if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* uniform over the CTA */
+    const bool masked = tri_partial(g.tri, m0, BM, n0, BN);
 
     /* acc[p][j]: rows (2p, 2p+1) of the thread's 8 rows, column j of its 8 columns */
     u64 acc[4][8];
@@ -227,7 +229,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c, int probe) {
           for (int e = 0; e < 4; e++) v[e] = accs[PACKED ? 0 : 4 * h + e][PACKED ? 0 : j];
         }
         float *p = C + m + n * g.ldc;
-        if (vec_c && m + 3 < g.m) {
+        if (vec_c && m + 3 < g.m && !masked) {
           float4 o = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
           if (use_beta) {
             float4 old = *reinterpret_cast<const float4 *>(p);
@@ -239,6 +241,7 @@ sgemm_ffma_kernel(DeviceGemm g, int vec_a, int vec_b, int vec_c, int probe) {
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             if (m + e >= g.m) break;
+            if (!tri_keep(g.tri, m + e, n)) continue;
             float o = alpha * v[e];
             if (use_beta) o = fmaf(beta, p[e], o);
             p[e] = o;
@@ -465,6 +468,7 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
     configured = true;
   }
   int64_t tiles = ((g.m + S::BM - 1) / S::BM) * ((g.n + S::BN - 1) / S::BN);
+  if (g.tri) tiles = tri_tile_count((g.m + S::BM - 1) / S::BM);
   int64_t cap = (int64_t)sm_count() * S::MINB;
   int grid = (int)(tiles < cap ? tiles : cap);
   const char *pv = getenv("B200_SGEMM_PROBE");
@@ -494,6 +498,7 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   if (packed < 0) { const char *ev = getenv("B200_SGEMM_PACKED"); packed = ev ? atoi(ev) : 1; }
   if (cfg < 0) { const char *ev = getenv("B200_SGEMM_CFG"); cfg = ev ? atoi(ev) : 0; }
   cudaError_t e;
+  if (g.tri && (g.m != g.n || cfg == 1 || packed != 1)) return cudaErrorNotSupported;   /* only the default kernels mask */
   if (cfg == 1) {
     if (a_mn && b_mn) e = launch_pw_variant<true, true>(g, stream, vec_a, vec_b, vec_c);
     else if (a_mn && !b_mn) e = launch_pw_variant<true, false>(g, stream, vec_a, vec_b, vec_c);
@@ -511,7 +516,8 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   const char *tv = getenv("B200_SGEMM_TILE");
   const int forced = tv ? atoi(tv) : 0;
   const int64_t sms = sm_count();
-  const int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+  int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
+  if (g.tri) { t128 = (t128 + 1) / 2; t64 = (t64 + 1) / 2; }
   const double penalty = (a_mn && b_mn) ? 1.15 : (!a_mn && !b_mn) ? 1e9 : 1.3;
   const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = penalty * (double)((t64 + sms - 1) / sms);   /* per-SM work */
   const bool small_tile = packed == 1 && (forced == 64 || (forced != 128 && est64 < est128));

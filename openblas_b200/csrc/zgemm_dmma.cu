@@ -215,6 +215,7 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
       int64_t bm, bn;
       banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
       const int64_t m0 = bm * BM, n0 = bn * BN;
+      if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* consumers skip the same tiles */
       for (int64_t kt = 0; kt < ktiles; kt++) {
         mbar_wait(empty_bar(slot), phase ^ 1);
         const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_ELEMS * 16), sb = sa + (uint32_t)(A_ELEMS * 16);
@@ -243,6 +244,7 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
     int64_t bm, bn;
     banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
+    if (tri_outside(g.tri, m0, BM, n0, BN)) continue;
 
     double re[4][4][2], im[4][4][2];
 #pragma unroll
@@ -293,7 +295,7 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int64_t m = m0 + wm + 8 * i + 2 * fk + h;
-          if (m >= g.m) continue;
+          if (m >= g.m || !tri_keep(g.tri, m, n)) continue;
           double2 *p = C + m + n * g.ldc;
           double xr = re[i][j][h], xi = im[i][j][h];
           double2 out;
@@ -351,6 +353,7 @@ cudaError_t launch_zgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
   static int cfg = -1;
   if (cfg < 0) { const char *ev = getenv("B200_ZGEMM_CFG"); cfg = ev ? atoi(ev) : 1; }
   cudaError_t e;
+  if (g.tri && cfg != 1) return cudaErrorNotSupported;       /* only the producer-warp kernel masks */
   if (cfg == 1) {
     if (a_mn && b_mn) e = launch_pw_variant<true, true>(g, stream);
     else if (a_mn && !b_mn) e = launch_pw_variant<true, false>(g, stream);

@@ -27,11 +27,14 @@ def test_level3_golden_vectors(ob, oracle):
     assert worst < 1.0
 
 
+@pytest.mark.parametrize("rankk_tri", ["1", "0"])
 @pytest.mark.parametrize("dtype", [cpu.S, cpu.D, cpu.CX, cpu.Z])
-def test_level3_all_flag_combinations(ob, oracle, dtype):
-    """Sizes that cross the block-column width of the rank-k path (128) and reach the fast GEMM
+def test_level3_all_flag_combinations(ob, oracle, dtype, rankk_tri, monkeypatch):
+    """Both rank-k schemes (B200_RANKK_TRI=1: the triangle masked inside the GEMM kernel, one launch per
+    product; =0: block columns with merged diagonal blocks).  Sizes that cross the block-column width of the rank-k path (128) and reach the fast GEMM
     kernels; NaN in the triangle of A that must not be read and in the triangle of C that must
     not be touched; beta == 0 over a NaN-filled triangle (C must not be read)."""
+    monkeypatch.setenv("B200_RANKK_TRI", rankk_tri)
     call = L.bind(ob.lib())
     rng = np.random.default_rng(300 + dtype)
     cplx = dtype in (cpu.CX, cpu.Z)
@@ -50,7 +53,8 @@ def test_level3_all_flag_combinations(ob, oracle, dtype):
                 for trans in (0, 1):
                     for (nn, k, beta_zero) in [(300, 90, False), (140, 33, True)]:
                         rows, cols = (k, nn) if trans else (nn, k)
-                        a, b = L.operand(rng, dtype, cols, rows + 1), L.operand(rng, dtype, cols, rows + 2)
+                        pa, pb = (2, 4) if nn == 300 else (1, 2)      # even leading dimensions at 300: DGEMM's masked kernel needs 16-byte columns
+                        a, b = L.operand(rng, dtype, cols, rows + pa), L.operand(rng, dtype, cols, rows + pb)
                         c0 = L.operand(rng, dtype, nn, nn + 3)
                         jj, ii = np.meshgrid(np.arange(nn), np.arange(nn + 3), indexing="ij")
                         if beta_zero:
@@ -59,10 +63,13 @@ def test_level3_all_flag_combinations(ob, oracle, dtype):
                             c0[((ii < jj) if uplo else (ii > jj)) & (ii < nn)] = np.nan
                         al = 0.7 if (herm and not x) or not cplx else 0.7 - 0.9j
                         be = 0.0 if beta_zero else (1.3 if herm or not cplx else 1.3 - 1.1j)
-                        case = (1, dtype, herm, x, uplo, trans, nn, nn, k, rows + 1, rows + 2, nn + 3, al, be)
+                        case = (1, dtype, herm, x, uplo, trans, nn, nn, k, rows + pa, rows + pb, nn + 3, al, be)
                         got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
                         L.check_case(case, got, want, gauge, K, touched, c0)
                         assert not np.isnan(got[touched]).any()
+                        if nn == 300:
+                            kern = ob.cblas.last_kernel()
+                            assert (kern in ("tri_merge",)) == (rankk_tri == "0"), kern
 
 
 def test_level3_scaling_only_paths(ob, oracle):
