@@ -75,9 +75,8 @@ __global__ void __launch_bounds__(256) tri_merge_kernel(int uplo, int herm, int6
 }
 
 /* ---------------------------------------------------------------------------------------------
- * tri_block_kernel: the base case of the recursive TRMM / TRSM (runtime_level3.inl).  One CTA of 64
- * threads takes one nb x nb (nb <= 64) diagonal block E and up to 64 right-hand sides, one per
- * thread, both staged in shared memory:
+ * tri_block_kernel: the base case of the recursive TRMM / TRSM (runtime_level3.inl).  One CTA takes
+ * one nb x nb (nb <= 64) diagonal block E and up to 32 right-hand sides, both staged in shared memory:
  *     SOLVE = false   x := alpha * E x         (rows bottom-up for a lower E, so it works in place)
  *     SOLVE = true    x := E^-1 (alpha * x)    by forward / backward substitution -- the reference's
  *                     trsm kernels substitute too (kernel/generic/trsm_kernel_LN.c `solve`), no
@@ -116,66 +115,90 @@ template <class T, class R> __device__ __forceinline__ T t_scalar(R re, R im) {
   if constexpr (Cx<T>::value) { T v; v.x = re; v.y = im; return v; } else { return (T)re; }
 }
 
-constexpr int TRI_NB = 64;      /* largest diagonal block; also the number of right-hand sides per CTA */
+constexpr int TRI_NB = 64;      /* largest diagonal block */
+constexpr int TRI_LANES = 8;    /* lanes that share one right-hand side (the dot products are split over them) */
+constexpr int TRI_RHS = 32;     /* right-hand sides per CTA: 256 threads */
+constexpr int TRI_LDE = TRI_NB + 1;
+constexpr int TRI_LDX = TRI_NB + 8;   /* X[rhs][k], stride = 8 (mod 32) elements: lane (rhs, q) reads word rhs*8 + q of a bank row */
 
+__device__ __forceinline__ float t_shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double t_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ float2 t_shfl_xor(float2 v, int m) { return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)); }
+__device__ __forceinline__ double2 t_shfl_xor(double2 v, int m) { return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)); }
+
+/* 256 threads: right-hand side c = thread / 8; the eight lanes of a group take the k = q, q+8, ... terms
+ * of every dot product and combine them with three shuffles.  The substitution is a chain of nb
+ * dependent steps, so what counts is the length of one step (ncu: one thread per right-hand side
+ * spent 66 us per 64 x 64 block, IPC 0.2, stalled on shared memory -- a third of a whole DTRSM):
+ * all loads of a row are issued together (fixed trip count, predicated), X is laid out so that
+ * they are conflict free, and the diagonal is inverted once while E is loaded, as the reference's
+ * packers do (kernel/generic/trsm_ltcopy_4.c stores INV(a)), so no division sits in the chain. */
 template <class T, class R, bool SOLVE>
-__global__ void __launch_bounds__(TRI_NB) tri_block_kernel(int nb, int64_t nrhs, int eff_lower, int unit, int cj, const T *__restrict__ f,
-                                                           int64_t fs_i, int64_t fs_k, R ar, R ai, T *__restrict__ b, int64_t rs, int64_t cs) {
+__global__ void __launch_bounds__(TRI_RHS * TRI_LANES) tri_block_kernel(int nb, int64_t nrhs, int eff_lower, int unit, int cj,
+                                                                        const T *__restrict__ f, int64_t fs_i, int64_t fs_k, R ar, R ai,
+                                                                        T *__restrict__ b, int64_t rs, int64_t cs) {
   extern __shared__ __align__(16) unsigned char tri_smem[];
-  constexpr int LD = TRI_NB + 1;
+  constexpr int NT = TRI_RHS * TRI_LANES;
   T *E = reinterpret_cast<T *>(tri_smem);
-  T *X = E + TRI_NB * LD;
-  const int t = threadIdx.x;
-  const int64_t c0 = (int64_t)blockIdx.x * TRI_NB;
-  for (int idx = t; idx < nb * nb; idx += TRI_NB) {
+  T *X = E + TRI_NB * TRI_LDE;
+  const int t = threadIdx.x, c = t / TRI_LANES, q = t % TRI_LANES;
+  const int64_t c0 = (int64_t)blockIdx.x * TRI_RHS;
+  if (nb < TRI_NB)      /* rows / columns beyond nb are read (and discarded) by the unrolled loop: keep them finite */
+    for (int idx = t; idx < TRI_NB * TRI_LDE + TRI_RHS * TRI_LDX; idx += NT) E[idx] = t_zero<T>();
+  __syncthreads();
+  for (int idx = t; idx < nb * nb; idx += NT) {
     const int i = fs_i == 1 ? idx % nb : idx / nb, k = fs_i == 1 ? idx / nb : idx % nb;
     T v = t_zero<T>();
-    if (i == k) v = unit ? t_one<T>() : f[i * fs_i + k * fs_k];
-    else if (eff_lower ? (k < i) : (k > i)) v = f[i * fs_i + k * fs_k];
+    if (i == k) {
+      v = unit ? t_one<T>() : f[i * fs_i + k * fs_k];
+      if (SOLVE && !unit) v = t_div(t_one<T>(), v);         /* 1 / diagonal; conj(1/z) = 1/conj(z) */
+    } else if (eff_lower ? (k < i) : (k > i)) {
+      v = f[i * fs_i + k * fs_k];
+    }
     if (cj) v = conj_of(v);
-    E[i * LD + k] = v;
+    E[i * TRI_LDE + k] = v;
   }
-  for (int idx = t; idx < nb * TRI_NB; idx += TRI_NB) {
-    const int r = rs == 1 ? idx % nb : idx / TRI_NB, c = rs == 1 ? idx / nb : idx % TRI_NB;
-    X[r * LD + c] = (c0 + c < nrhs) ? b[r * rs + (c0 + c) * cs] : t_zero<T>();
+  for (int idx = t; idx < nb * TRI_RHS; idx += NT) {
+    const int r = rs == 1 ? idx % nb : idx / TRI_RHS, cc = rs == 1 ? idx / nb : idx % TRI_RHS;
+    X[cc * TRI_LDX + r] = (c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : t_zero<T>();
   }
   __syncthreads();
-  if (c0 + t < nrhs) {
+  {   /* every lane takes part (shuffles); right-hand sides beyond nrhs hold zeros */
     const T alpha = t_scalar<T, R>(ar, ai);
-    if (!SOLVE) {
-      if (eff_lower) {
-        for (int i = nb - 1; i >= 0; i--) {
-          T acc = t_zero<T>();
-          for (int k = 0; k <= i; k++) acc = t_add(acc, t_mul(E[i * LD + k], X[k * LD + t]));
-          X[i * LD + t] = t_mul(alpha, acc);
-        }
-      } else {
-        for (int i = 0; i < nb; i++) {
-          T acc = t_zero<T>();
-          for (int k = i; k < nb; k++) acc = t_add(acc, t_mul(E[i * LD + k], X[k * LD + t]));
-          X[i * LD + t] = t_mul(alpha, acc);
+    T *xc = X + c * TRI_LDX;
+    for (int ii = 0; ii < nb; ii++) {
+      /* row order: a product overwrites x_i after its last use, a solve needs the x_k it depends on */
+      const int i = (SOLVE == (eff_lower != 0)) ? ii : nb - 1 - ii;
+      const int k_lo = eff_lower ? 0 : (SOLVE ? i + 1 : i), k_hi = eff_lower ? (SOLVE ? i : i + 1) : nb;
+      const T *ei = E + i * TRI_LDE;
+      T acc = t_zero<T>(), acc2 = t_zero<T>();
+#pragma unroll
+      for (int j = 0; j < TRI_NB / TRI_LANES; j += 2) {
+        const int k0 = q + j * TRI_LANES, k1 = k0 + TRI_LANES;
+        const T e0 = ei[k0], x0 = xc[k0];                 /* k < 64 always: inside the arrays */
+        const T e1 = ei[k1], x1 = xc[k1];
+        if (k0 >= k_lo && k0 < k_hi) acc = t_add(acc, t_mul(e0, x0));
+        if (k1 >= k_lo && k1 < k_hi) acc2 = t_add(acc2, t_mul(e1, x1));
+      }
+      acc = t_add(acc, acc2);
+      acc = t_add(acc, t_shfl_xor(acc, 1));
+      acc = t_add(acc, t_shfl_xor(acc, 2));
+      acc = t_add(acc, t_shfl_xor(acc, 4));
+      if (q == 0) {
+        if (SOLVE) {
+          const T v = t_sub(t_mul(alpha, xc[i]), acc);
+          xc[i] = unit ? v : t_mul(v, ei[i]);
+        } else {
+          xc[i] = t_mul(alpha, acc);
         }
       }
-    } else {
-      if (eff_lower) {
-        for (int i = 0; i < nb; i++) {
-          T acc = t_mul(alpha, X[i * LD + t]);
-          for (int k = 0; k < i; k++) acc = t_sub(acc, t_mul(E[i * LD + k], X[k * LD + t]));
-          X[i * LD + t] = unit ? acc : t_div(acc, E[i * LD + i]);
-        }
-      } else {
-        for (int i = nb - 1; i >= 0; i--) {
-          T acc = t_mul(alpha, X[i * LD + t]);
-          for (int k = i + 1; k < nb; k++) acc = t_sub(acc, t_mul(E[i * LD + k], X[k * LD + t]));
-          X[i * LD + t] = unit ? acc : t_div(acc, E[i * LD + i]);
-        }
-      }
+      __syncwarp();
     }
   }
   __syncthreads();
-  for (int idx = t; idx < nb * TRI_NB; idx += TRI_NB) {
-    const int r = rs == 1 ? idx % nb : idx / TRI_NB, c = rs == 1 ? idx / nb : idx % TRI_NB;
-    if (c0 + c < nrhs) b[r * rs + (c0 + c) * cs] = X[r * LD + c];
+  for (int idx = t; idx < nb * TRI_RHS; idx += NT) {
+    const int r = rs == 1 ? idx % nb : idx / TRI_RHS, cc = rs == 1 ? idx / nb : idx % TRI_RHS;
+    if (c0 + cc < nrhs) b[r * rs + (c0 + cc) * cs] = X[cc * TRI_LDX + r];
   }
 }
 
@@ -184,13 +207,13 @@ cudaError_t tri_block_t(int nb, int64_t nrhs, int eff_lower, int unit, int cj, c
                         double ai, void *b, int64_t rs, int64_t cs, cudaStream_t s) {
   static bool configured = false;
   auto kern = tri_block_kernel<T, R, SOLVE>;
-  const size_t smem = 2 * (size_t)TRI_NB * (TRI_NB + 1) * sizeof(T);
+  const size_t smem = ((size_t)TRI_NB * TRI_LDE + (size_t)TRI_RHS * TRI_LDX) * sizeof(T);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<(unsigned)((nrhs + TRI_NB - 1) / TRI_NB), TRI_NB, smem, s>>>(nb, nrhs, eff_lower, unit, cj, (const T *)f, fs_i, fs_k, (R)ar, (R)ai,
+  kern<<<(unsigned)((nrhs + TRI_RHS - 1) / TRI_RHS), TRI_RHS * TRI_LANES, smem, s>>>(nb, nrhs, eff_lower, unit, cj, (const T *)f, fs_i, fs_k, (R)ar, (R)ai,
                                                                        (T *)b, rs, cs);
   return cudaGetLastError();
 }
