@@ -1,5 +1,8 @@
 #!/bin/bash
-# BASELINE.json configs through the reference's own harness and bench.py; outputs in gpurun_out/.
+# TEST INFRASTRUCTURE (lives under tests/ because it executes binaries from oracle/_ref/): BASELINE.json
+# configs through the reference's own benchmark/gemm.c harness -- once linked against libopenblas_b200.so,
+# once against the reference itself on the host cores -- and through bench.py; outputs in gpurun_out/.
+# The run recorded in profiles/r01_config1_reference_harness.txt came from this script.
 set -u
 mkdir -p gpurun_out
 B=oracle/_ref/bench
