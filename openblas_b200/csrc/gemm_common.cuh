@@ -40,7 +40,7 @@ __host__ __device__ __forceinline__ bool tri_partial(int tri, int64_t m0, int bm
  * lower triangle, mirrored for the upper one), so the static round-robin over persistent CTAs stays
  * balanced; kernels with rectangular tiles walk all tiles and skip with tri_outside(). */
 __host__ __device__ __forceinline__ int64_t tri_tile_count(int64_t nt) { return nt * (nt + 1) / 2; }
-__device__ __forceinline__ void tri_tile_coords(int64_t u, int tri, int64_t &bm, int64_t &bn) {
+__host__ __device__ __forceinline__ void tri_tile_coords(int64_t u, int tri, int64_t &bm, int64_t &bn) {
   int64_t r = (int64_t)((sqrt(8.0 * (double)u + 1.0) - 1.0) * 0.5);
   while (r * (r + 1) / 2 > u) r--;
   while ((r + 1) * (r + 2) / 2 <= u) r++;
