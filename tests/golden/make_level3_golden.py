@@ -11,6 +11,8 @@ been built from it by oracle/build_ref.py (GENERIC target, one thread: determini
   trxm_golden.npz                   the same for TRMM / TRSM: every side / uplo / trans / diag combination
   errexit_level3_reference.txt      what the reference's entry points hand to xerbla_ for the
                                     table of illegal calls in tests/c/errexit_level3.c
+  errexit_fuzz_reference.txt        the same for the 4000 fixed-seed random calls of tests/c/errexit_fuzz.c
+                                    (GEMM included)
 """
 import os
 import subprocess
@@ -136,6 +138,13 @@ def main():
         text = subprocess.check_output([exe], text=True)
     open(os.path.join(OUT, "errexit_level3_reference.txt"), "w").write(text)
     print("errexit_level3_reference.txt:", len(text.splitlines()), "probes")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "errexit_fuzz")
+        subprocess.check_call(["gcc", "-O1", "-Wall", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", "errexit_fuzz.c"),
+                               "-o", exe, f"-L{refdir}", "-lopenblas_ref", f"-Wl,-rpath,{refdir}"])
+        text = subprocess.check_output([exe], text=True)
+    open(os.path.join(OUT, "errexit_fuzz_reference.txt"), "w").write(text)
+    print("errexit_fuzz_reference.txt:", len(text.splitlines()), "probes")
 
 
 if __name__ == "__main__":

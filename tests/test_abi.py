@@ -98,6 +98,23 @@ def test_default_xerbla_prints_reference_message(ob, capfd):
     assert " ** On entry to DGEMM  parameter number  4 had an illegal value" in out
 
 
+def test_random_argument_probes_match_the_reference(tmp_path, ob):
+    """tests/c/errexit_fuzz.c: 4000 fixed-seed random calls over every level-3 entry point (both ABIs,
+    both orders and an illegal one, legal and illegal flags / extents / leading dimensions); every legal
+    call is a no-op, so nothing is computed and no GPU is needed.  Output must equal, byte for byte,
+    what the same program printed when linked against the reference."""
+    exe = tmp_path / "errexit_fuzz"
+    subprocess.check_call(["gcc", "-O1", "-Wall", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", "errexit_fuzz.c"),
+                           "-o", str(exe), f"-L{LIBDIR}", "-lopenblas_b200", f"-Wl,-rpath,{LIBDIR}"])
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    want = open(os.path.join(ROOT, "tests", "golden", "errexit_fuzz_reference.txt")).read()
+    assert len(want.splitlines()) == 4000
+    got, exp = r.stdout.splitlines(), want.splitlines()
+    bad = [(g, e) for g, e in zip(got, exp) if g != e]
+    assert not bad and len(got) == len(exp), bad[:5]
+
+
 def test_triangle_tile_enumeration_on_host(tmp_path):
     """The SYRK family runs as ONE GEMM launch whose kernels enumerate only the tiles of the triangle
     (gemm_common.cuh).  tests/c/tri_tiles.cu checks on the host that the closed-form index -> (row, col)
