@@ -21,7 +21,7 @@ oracle/ref_loader.py picks the best target the host CPU supports at run time (th
 CPU differs from the authoring container's).  Outputs are git-ignored but travel with gpurun.
 """
 import concurrent.futures as cf
-import os, shlex, subprocess, sys
+import os, shlex, shutil, subprocess, sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("OPENBLAS_REFERENCE", "/root/reference")
@@ -120,6 +120,8 @@ def build_ctest(lib_dir, base):
             extra += ["-DCOMPLEX"] if p in "cz" else []
             run([CC] + flags + extra + ["-c", os.path.join(src, f), "-o", o])
             objs.append(o)
+        # the driver's input file, unchanged, next to the binary (oracle/_ref/ is not part of the history)
+        shutil.copyfile(os.path.join(src, f"{p}in3"), os.path.join(cdir, f"{p}in3"))
         exe = os.path.join(cdir, f"x{p}cblat3")
         run([CC, "-o", exe] + objs + [stub_c, f"-L{lib_dir}", "-lopenblas_b200",
                                        f"-Wl,-rpath,$ORIGIN/../../../openblas_b200/lib", "-lm", "-lpthread"])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Writes tests/golden/gemm_golden.npz and tests/golden/ctest_in3/*: fixtures produced by the
+"""Writes tests/golden/gemm_golden.npz and bf16_golden.npz: fixtures produced by the
 REFERENCE itself (run in the authoring container, where /root/reference is mounted and
 oracle/_ref has been built from it by oracle/build_ref.py).
 
@@ -8,7 +8,6 @@ oracle/_ref has been built from it by oracle/build_ref.py).
                     ragged shapes, padded leading dimensions and the ctest alpha/beta values.
                     The oracle must reproduce these bit for bit; the GPU path within the bound.
   bf16_golden.npz   fp32 -> bf16 -> fp32 conversions by the reference's sbstobf16_/sbf16tos_.
-  ctest_in3/?in3    the reference's ctest input files (ctest/{s,d,c,z}in3), every routine enabled.
 """
 import ctypes as C
 import os
@@ -89,18 +88,6 @@ def main():
     lib.sbf16tos_(C.byref(n), h.ctypes.data_as(C.c_void_p), C.byref(one), back.ctypes.data_as(C.c_void_p), C.byref(one))
     np.savez_compressed(os.path.join(OUT, "bf16_golden.npz"), x=x, bf16=h, back=back)
     print("bf16_golden.npz:", x.size, "values")
-
-    os.makedirs(os.path.join(OUT, "ctest_in3"), exist_ok=True)
-    for p in "sdcz":
-        lines = open(os.path.join(REF, "ctest", f"{p}in3")).read().splitlines()
-        res = []
-        for ln in lines:
-            if False:      # every routine of the level-3 driver is implemented by the library: nothing is switched off
-                name, rest = ln.split(None, 1)
-                ln = f"{name:<12s} F" + rest[1:]
-            res.append(ln)
-        open(os.path.join(OUT, "ctest_in3", f"{p}in3"), "w").write("\n".join(res) + "\n")
-    print("ctest_in3 written")
 
 
 if __name__ == "__main__":

@@ -3,8 +3,8 @@ drop-in (oracle/build_ref.py compiles ctest/c_?blat3c.c, c_?blas3.c, c_?3chke.c,
 /root/reference and links them first against our library): 27 783 cblas_?gemm calls per layout
 for s/d/z (17 496 for c), the SYMM/HEMM, SYRK/HERK, SYR2K/HER2K, TRMM and TRSM sweeps, and the error-exit
 checks of all of them, each judged by the reference's own checkers (DMMCH and friends).
-Inputs: the reference's ?in3 files, every routine enabled
-(tests/golden/ctest_in3, written by tests/golden/make_golden.py)."""
+Inputs: the reference's own ?in3 files, every routine enabled (oracle/build_ref.py puts them next
+to the binaries under oracle/_ref/ctest/)."""
 import os
 import subprocess
 
@@ -20,7 +20,7 @@ def test_ctest_level3_gemm(p):
     exe = os.path.join(CTEST, f"x{p}cblat3")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/ctest not built (needs /root/reference at build time)")
-    with open(os.path.join(ROOT, "tests", "golden", "ctest_in3", f"{p}in3")) as f:
+    with open(os.path.join(CTEST, f"{p}in3")) as f:      # the reference's own input file, copied by oracle/build_ref.py
         r = subprocess.run([exe], stdin=f, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     out = r.stdout
     print(out[-3000:])
