@@ -1,4 +1,4 @@
-"""CPU tests of the multi-GPU layer's HOST logic (openblas_b200/summa.py) with 2 processes on the
+"""CPU tests of the multi-GPU layer's HOST logic (openblas_b200/summa.py) with 2, 4 and 8 processes on the
 gloo backend: grid shape, block-cyclic ownership maps, the panel schedule, and a full SUMMA sweep
 whose local product is done by the CPU oracle (test-only injection; on GPUs it is the library's
 b200_gemm_async).  The distributed result must equal the single-process oracle result."""
@@ -87,10 +87,12 @@ def _worker(rank, world, port, m, n, k, nb, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape", [(37, 29, 23, 4), (16, 16, 16, 8), (5, 40, 9, 3)])
-def test_summa_two_ranks_gloo_matches_oracle(shape):
+@pytest.mark.parametrize("world,shape", [(2, (37, 29, 23, 4)), (2, (16, 16, 16, 8)), (2, (5, 40, 9, 3)),
+                                         (4, (37, 29, 23, 4)), (4, (9, 7, 30, 2)), (8, (41, 53, 19, 3))])
+def test_summa_gloo_matches_oracle(world, shape):
+    """1 x 2, 2 x 2 and 2 x 4 process grids (the grids bench.py runs at N = 2, 4, 8): both broadcast
+    directions, ranks that own no block of a short dimension, ragged last blocks."""
     m, n, k, nb = shape
-    world = 2
     port = _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
