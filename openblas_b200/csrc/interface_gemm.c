@@ -199,8 +199,9 @@ static void run_batch(int dtype, int order, const enum CBLAS_TRANSPOSE *ta_arr,
   int cplx = b200_is_complex(dtype);
   size_t scalar = b200_out_size(dtype);
   for (blasint g = 0; g < group_count; g++) total += group_size[g];
-  if (total <= 0) return;
-  b200_problem *probs = (b200_problem *)malloc((size_t)total * sizeof(b200_problem));
+  /* no early return for an empty batch: the reference still validates every group of it
+   * (gemm_batch.c:152-158 allocates, :186-287 checks group by group whatever the group sizes are) */
+  b200_problem *probs = (b200_problem *)malloc((size_t)(total > 0 ? total : 1) * sizeof(b200_problem));
   if (!probs) { fprintf(stderr, "openblas_b200: gemm_batch: out of host memory\n"); return; }
 
   for (blasint g = 0; g < group_count; idx += group_size[g], g++) {

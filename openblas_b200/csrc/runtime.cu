@@ -699,6 +699,16 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
 }
 
 B200_HIDDEN int b200_run_batch(const b200_problem *p, int64_t count) {
+  {  /* a batch made only of C := 1 * C + 0 members has nothing to do: return before CUDA is touched */
+    bool any = false;
+    for (int64_t i = 0; i < count && !any; i++) {
+      DeviceGemm g;
+      read_scalars(&p[i], g);
+      const bool product = p[i].k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
+      any = product || !(g.beta_re == 1.0 && g.beta_im == 0.0);
+    }
+    if (!any) return 0;
+  }
   ContextLease lease;
   int err = acquire(&lease.c);
   if (err) return err;

@@ -47,7 +47,7 @@ int main(void) {
   for (int i = 0; i < 64; i++) c[i] = 42.0;
 
   for (int it = 0; it < 4000; it++) {
-    const int fam = (int)rnd(9), prec = (int)rnd(4), f77 = rnd(4) == 0;
+    const int fam = (int)rnd(10), prec = (int)rnd(4), f77 = rnd(4) == 0;
     const enum CBLAS_ORDER o = (enum CBLAS_ORDER)pick(orders, 5);
     const enum CBLAS_TRANSPOSE ta = (enum CBLAS_TRANSPOSE)pick(transes, 6), tb = (enum CBLAS_TRANSPOSE)pick(transes, 6);
     const enum CBLAS_SIDE sd = (enum CBLAS_SIDE)pick(sides, 5);
@@ -56,7 +56,7 @@ int main(void) {
     blasint m = pick(dims, 6), n = pick(dims, 6), k = pick(dims, 6), lda = pick(lds, 6), ldb = pick(lds, 6), ldc = pick(lds, 6);
     char cta = tch[rnd(8)], ctb = tch[rnd(8)], cs = sch[rnd(5)], cu = uch[rnd(5)], cd = dch[rnd(5)];
     const char *what = "?";
-    if (fam >= 7 && m > 0 && n > 0) { if (rnd(2)) m = 0; else n = 0; }     /* TRMM / TRSM: legal calls must be empty */
+    if ((fam == 7 || fam == 8) && m > 0 && n > 0) { if (rnd(2)) m = 0; else n = 0; }     /* TRMM / TRSM: legal calls must be empty */
     /* scalars: alpha = 0 (real or complex), beta = 1 */
 #define AL (prec == 0 ? (void *)&s0 : prec == 1 ? (void *)&d0 : prec == 2 ? (void *)c0 : (void *)z0)
 #define BE (prec == 0 ? (void *)&s1 : prec == 1 ? (void *)&d1 : prec == 2 ? (void *)c1 : (void *)z1)
@@ -75,11 +75,11 @@ int main(void) {
           else cblas_zgemm(o, ta, tb, m, n, k, z0, a, lda, b, ldb, z1, c, ldc);
         }
         break;
-      case 1:   /* SBGEMM, and complex GEMM once more with the two op arguments drawn the other way round */
-        what = "sbgemm/gemm";
+      case 1:   /* SBGEMM / GEMM3M */
+        what = "sbgemm/gemm3m";
         if (prec < 2) cblas_sbgemm(o, ta, tb, m, n, k, 0.f, (bfloat16 *)a, lda, (bfloat16 *)b, ldb, 1.f, (float *)c, ldc);
-        else if (prec == 2) cblas_cgemm(o, tb, ta, m, n, k, c0, a, lda, b, ldb, c1, c, ldc);
-        else cblas_zgemm(o, tb, ta, m, n, k, z0, a, lda, b, ldb, z1, c, ldc);
+        else if (prec == 2) cblas_cgemm3m(o, ta, tb, m, n, k, c0, a, lda, b, ldb, c1, c, ldc);
+        else cblas_zgemm3m(o, ta, tb, m, n, k, z0, a, lda, b, ldb, z1, c, ldc);
         break;
       case 2:   /* SYMM */
         what = "symm";
@@ -128,6 +128,19 @@ int main(void) {
           else { if (fam == 5) cblas_zsyr2k(o, up, ta, n, k, z0, a, lda, b, ldb, z1, c, ldc); else cblas_zher2k(o, up, ta, n, k, z0, a, lda, b, ldb, 1.0, c, ldc); }
         }
         break;
+      case 9: { /* GEMM_BATCH: up to two groups, the second one drawn independently; a bad group aborts the call */
+        what = "gemm_batch";
+        enum CBLAS_TRANSPOSE tas[2] = {ta, (enum CBLAS_TRANSPOSE)pick(transes, 6)}, tbs[2] = {tb, (enum CBLAS_TRANSPOSE)pick(transes, 6)};
+        blasint ms[2] = {m, pick(dims, 6)}, ns[2] = {n, pick(dims, 6)}, ks[2] = {k, pick(dims, 6)};
+        blasint las[2] = {lda, pick(lds, 6)}, lbs[2] = {ldb, pick(lds, 6)}, lcs[2] = {ldc, pick(lds, 6)};
+        blasint gs[2] = {(blasint)rnd(3), (blasint)rnd(3)}, gc = (blasint)rnd(3);
+        const void *ap[4] = {a, a, a, a}, *bp[4] = {b, b, b, b}; void *cp[4] = {c, c, c, c};
+        if (prec == 0) { float al[2] = {0, 0}, be[2] = {1, 1}; cblas_sgemm_batch(o, tas, tbs, ms, ns, ks, al, (const float **)ap, las, (const float **)bp, lbs, be, (float **)cp, lcs, gc, gs); }
+        else if (prec == 1) { double al[2] = {0, 0}, be[2] = {1, 1}; cblas_dgemm_batch(o, tas, tbs, ms, ns, ks, al, (const double **)ap, las, (const double **)bp, lbs, be, (double **)cp, lcs, gc, gs); }
+        else if (prec == 2) { float al[4] = {0, 0, 0, 0}, be[4] = {1, 0, 1, 0}; cblas_cgemm_batch(o, tas, tbs, ms, ns, ks, al, ap, las, bp, lbs, be, cp, lcs, gc, gs); }
+        else { double al[4] = {0, 0, 0, 0}, be[4] = {1, 0, 1, 0}; cblas_zgemm_batch(o, tas, tbs, ms, ns, ks, al, ap, las, bp, lbs, be, cp, lcs, gc, gs); }
+        break;
+      }
       default:  /* 7: TRMM, 8: TRSM */
         what = fam == 7 ? "trmm" : "trsm";
         if (f77) {
