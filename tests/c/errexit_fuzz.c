@@ -9,6 +9,7 @@
  * libopenblas_b200.so it must print the same bytes (tests/test_abi.py).
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "openblas_b200.h"
 
@@ -28,8 +29,10 @@ static unsigned rnd(unsigned n) {
 }
 static int pick(const int *set, int n) { return set[rnd((unsigned)n)]; }
 
-int main(void) {
+int main(int argc, char **argv) {
   static double a[64], b[64], c[64];
+  const int iterations = argc > 1 ? atoi(argv[1]) : 4000;          /* defaults = the committed fixture */
+  if (argc > 2) state ^= strtoull(argv[2], NULL, 0) * 0xD6E8FEB86659FD93ull;
   static const int orders[] = {CblasColMajor, CblasRowMajor, CblasColMajor, CblasRowMajor, 0};
   static const int transes[] = {CblasNoTrans, CblasTrans, CblasConjTrans, CblasConjNoTrans, 0, 7};
   static const int sides[] = {CblasLeft, CblasRight, CblasLeft, CblasRight, 0};
@@ -46,7 +49,7 @@ int main(void) {
   double d0 = 0, d1 = 1; float s0 = 0, s1 = 1;
   for (int i = 0; i < 64; i++) c[i] = 42.0;
 
-  for (int it = 0; it < 4000; it++) {
+  for (int it = 0; it < iterations; it++) {
     const int fam = (int)rnd(10), prec = (int)rnd(4), f77 = rnd(4) == 0;
     const enum CBLAS_ORDER o = (enum CBLAS_ORDER)pick(orders, 5);
     const enum CBLAS_TRANSPOSE ta = (enum CBLAS_TRANSPOSE)pick(transes, 6), tb = (enum CBLAS_TRANSPOSE)pick(transes, 6);

@@ -115,6 +115,25 @@ def test_random_argument_probes_match_the_reference(tmp_path, ob):
     assert not bad and len(got) == len(exp), bad[:5]
 
 
+def test_random_argument_probes_live_against_reference(tmp_path, ob):
+    """When oracle/_ref is present: the same program with other seeds, 2 x 50 000 calls, run against the
+    reference and against the library side by side (1 000 000 calls were compared this way when the
+    fixture was made)."""
+    from oracle import cpu
+    if not cpu.have_reference("generic"):
+        pytest.skip("oracle/_ref not built")
+    refdir = os.path.dirname(cpu.ref_path("generic"))
+    src = os.path.join(ROOT, "tests", "c", "errexit_fuzz.c")
+    ours, ref = tmp_path / "fz_ours", tmp_path / "fz_ref"
+    subprocess.check_call(["gcc", "-O1", f"-I{ROOT}/include", src, "-o", str(ours), f"-L{LIBDIR}", "-lopenblas_b200", f"-Wl,-rpath,{LIBDIR}"])
+    subprocess.check_call(["gcc", "-O1", f"-I{ROOT}/include", src, "-o", str(ref), f"-L{refdir}", "-lopenblas_ref", f"-Wl,-rpath,{refdir}"])
+    for seed in ("11", "12"):
+        a = subprocess.run([str(ours), "50000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
+        b = subprocess.run([str(ref), "50000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
+        assert a.returncode == 0 and b.returncode == 0
+        assert a.stdout == b.stdout, [(x, y) for x, y in zip(a.stdout.splitlines(), b.stdout.splitlines()) if x != y][:5]
+
+
 def test_triangle_tile_enumeration_on_host(tmp_path):
     """The SYRK family runs as ONE GEMM launch whose kernels enumerate only the tiles of the triangle
     (gemm_common.cuh).  tests/c/tri_tiles.cu checks on the host that the closed-form index -> (row, col)
