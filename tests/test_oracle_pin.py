@@ -291,3 +291,41 @@ def test_trxm_argument_checks_match_reference_error_exits(oracle):
     assert oracle.check_trxm(1, 0, 0, 0, 0, 2, 1, 2, -1) == want["dtrmm lda right n=2"] == 9
     assert oracle.check_trxm(0, 1, 3, 0, 2, 0, 2, 1, -1) == want["dtrmm ldb m=2"] == 11
     assert oracle.check_trxm(-1, 0, 0, 0, 2, 3, 1, 1, -1) == want["dtrmm side + others"] == 1
+
+
+@pytest.mark.skipif(not cpu.have_reference("generic"), reason="oracle/_ref not built")
+def test_gemm_batch_reference_equals_small_matrix_oracle_bitwise(oracle):
+    """the reference's cblas_dgemm_batch (interface/gemm_batch.c) sends matrices that pass
+    GEMM_SMALL_MATRIX_PERMIT to the small-matrix kernels; per matrix its GENERIC build must equal the
+    oracle's restatement of those kernels bit for bit, and sit within the bound of the blocked oracle."""
+    import ctypes as C
+    ref = cpu.Reference("generic")
+    ref.set_threads(1)
+    rng = np.random.default_rng(4)
+    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2), (0, 0, 64, 48, 130, 2)]
+    alphas, betas = [0.7, 1.0, -0.4], [1.3, 0.0, 1.0]
+    cb = {0: 111, 1: 112}
+    probs = []
+    for (ta, tb, m, n, k, cnt) in groups:
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, ta, tb, m, n, k, pad=(1, 1, 1))
+            probs.append((a, lda, b, ldb, c0, c0.copy(), ldc))
+    ints = lambda v: (C.c_int * len(v))(*v)
+    first = [sum(g[5] for g in groups[:i]) for i in range(len(groups))]
+    ptrs = lambda j: (C.c_void_p * len(probs))(*[p[j].ctypes.data for p in probs])
+    ref.lib.cblas_dgemm_batch(102, ints([cb[g[0]] for g in groups]), ints([cb[g[1]] for g in groups]), ints([g[2] for g in groups]),
+                              ints([g[3] for g in groups]), ints([g[4] for g in groups]), (C.c_double * 3)(*alphas), ptrs(0),
+                              ints([probs[f][1] for f in first]), ptrs(2), ints([probs[f][3] for f in first]),
+                              (C.c_double * 3)(*betas), ptrs(5), ints([probs[f][6] for f in first]), len(groups),
+                              ints([g[5] for g in groups]))
+    i = 0
+    for gi, (ta, tb, m, n, k, cnt) in enumerate(groups):
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, got, ldc = probs[i]
+            i += 1
+            small = c0.copy()
+            oracle.gemm(cpu.D, ta, tb, m, n, k, alphas[gi], a, lda, b, ldb, betas[gi], small, ldc, small=True)
+            assert np.array_equal(small.view(np.uint8), got.view(np.uint8)), (gi, m, n, k)
+            blocked = c0.copy()
+            oracle.gemm(cpu.D, ta, tb, m, n, k, alphas[gi], a, lda, b, ldb, betas[gi], blocked, ldc)
+            assert oracle.ratio(cpu.D, ta, tb, m, n, k, alphas[gi], a, lda, b, ldb, betas[gi], c0, ldc, got, ldc, blocked, ldc) <= C_BOUND
