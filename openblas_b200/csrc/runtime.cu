@@ -27,6 +27,30 @@
 
 namespace b200 {
 
+/* Size thresholds of the host staging paths.  B200_HOSTSIM (tests/hostsim: this file compiled by the
+ * host compiler against a host-memory stand-in for the CUDA runtime and CPU stand-ins for the kernels,
+ * to test the staging / scheduling logic without a GPU) shrinks them so that every path is reached
+ * with matrices a CPU oracle can multiply; the product build never defines it. */
+#ifdef B200_HOSTSIM
+#define B200_SMALL_BYTES   ((size_t)16 << 10)
+#define B200_SLOT_BYTES    ((size_t)8 << 10)
+#define B200_PANEL_MIN     32
+#define B200_PANEL_BIG     64
+#define B200_PANEL_BIG_AT  256
+#define B200_PIPE_BYTES    ((size_t)64 << 10)
+#define B200_BATCH_BYTES   ((size_t)256 << 10)
+#define B200_POOL_BYTES    ((size_t)4 << 10)
+#else
+#define B200_SMALL_BYTES   ((size_t)4 << 20)
+#define B200_SLOT_BYTES    ((size_t)32 << 20)
+#define B200_PANEL_MIN     2048
+#define B200_PANEL_BIG     4096
+#define B200_PANEL_BIG_AT  8192
+#define B200_PIPE_BYTES    ((size_t)128 << 20)
+#define B200_BATCH_BYTES   ((size_t)64 << 20)
+#define B200_POOL_BYTES    ((size_t)16 << 20)
+#endif
+
 /* ---------------------------------------------------------------- process-wide state */
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_forced_kernel{B200_K_AUTO};
@@ -221,7 +245,7 @@ struct Operand {
  * host operand into ONE pinned block, one H2D, one kernel, one D2H, then copy only the
  * m x n window of C back so padding rows of the caller's C stay bit-identical
  * (ctest LDERES, c_dblat3.f:2352-2412). */
-static const size_t kSmallBytes = 4u << 20;
+static const size_t kSmallBytes = B200_SMALL_BYTES;
 
 static void pack_to(char *dst, const Operand &o) {
   size_t row_bytes = (size_t)o.rows * o.es;
@@ -234,7 +258,7 @@ static void pack_to(char *dst, const Operand &o) {
  * at a few GB/s on one thread; instead the columns are copied into pinned slots by a small pool of
  * host threads (the reference uses all cores for the GEMM itself; we only borrow a few for memcpy)
  * while the previous slot is in flight on the DMA engine. */
-static const size_t kSlotBytes = 32u << 20;
+static const size_t kSlotBytes = B200_SLOT_BYTES;
 
 class HostPool {
  public:
@@ -288,7 +312,7 @@ static void host_copy_cols(char *dst, size_t dpitch, const char *src, size_t spi
   /* waking sleeping pool threads costs up to milliseconds on a virtualised host (measured: a 1024^3
    * DGEMM call went from 2 ms to 16 ms when its 8 MB operands were split over the pool), so only
    * copies of at least 16 MB are shared out */
-  int64_t parts = total >= (16u << 20) ? (int64_t)(total / (2u << 20)) : 1;
+  int64_t parts = total >= B200_POOL_BYTES ? (int64_t)(total / (B200_POOL_BYTES / 8)) : 1;
   if (parts > 16) parts = 16;
   if ((size_t)parts > cols) parts = (int64_t)cols;
   if (parts < 1) parts = 1;
@@ -377,12 +401,12 @@ static int d2h_any(Context *ctx, cudaStream_t s, PtrKind kind, char *host, size_
  * D2H stream -- so after the first pair of panels the PCIe transfers in both directions hide
  * behind the GEMMs (the reference, being a CPU library, has no such phase; this is what makes the
  * host-pointer BLAS call approach the device-resident rate). */
-static const int64_t kPanelMin = 2048;   /* smallest block edge; see panel_edge() */
+static const int64_t kPanelMin = B200_PANEL_MIN;   /* smallest block edge; see panel_edge() */
 
 /* Block edge of the pipeline: 2048 gives the earliest start (first A and B panels are small) but a
  * 2048 x 2048 block is only 256 C tiles = 1.7 waves of 148 CTAs (86 % efficient); 4096 gives 1024 tiles
  * = 6.9 waves.  Use the larger block once the problem has enough of them to keep the pipe busy. */
-static int64_t panel_edge(int64_t m, int64_t n) { return (m >= 8192 && n >= 8192) ? 4096 : 2048; }
+static int64_t panel_edge(int64_t m, int64_t n) { return (m >= B200_PANEL_BIG_AT && n >= B200_PANEL_BIG_AT) ? B200_PANEL_BIG : B200_PANEL_MIN; }
 
 static int event_at(Context *ctx, size_t i, cudaEvent_t *out) {
   while (ctx->events.size() <= i) {
@@ -560,7 +584,7 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
     return 0;
   }
 
-  if (product && p->m >= 2 * kPanelMin && p->n >= 2 * kPanelMin && need >= (128u << 20)) return run_pipelined(ctx, p, g, A, B, C, use_beta);
+  if (product && p->m >= 2 * kPanelMin && p->n >= 2 * kPanelMin && need >= B200_PIPE_BYTES) return run_pipelined(ctx, p, g, A, B, C, use_beta);
 
   /* large host operands: strided DMA straight from / to the caller's memory (full PCIe
    * rate when it is pinned; staged by the driver when it is pageable) */
@@ -659,7 +683,7 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
     }
   }
   const size_t total = ab_bytes + c_bytes;
-  if (total > (64u << 20)) return 0;
+  if (total > B200_BATCH_BYTES) return 0;
   int err = reserve_device(ctx, total);
   if (err) return err;
   if ((err = reserve_pinned(ctx, total))) return err;

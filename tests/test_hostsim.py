@@ -1,0 +1,268 @@
+"""CPU tests of the library's HOST logic with no GPU: tests/hostsim/build.sh compiles the unchanged
+interface_*.c and runtime.cu (with g++, -DB200_HOSTSIM: smaller size thresholds so that every staging
+path is reached by matrices a CPU can multiply) against a host-memory stand-in for the CUDA runtime
+(cuda_shim.cpp: "device" memory is poisoned with NaN bytes) and CPU stand-ins for the kernel launchers
+(sim_kernels.cpp: every GEMM launch is the oracle, which is bit-identical to the reference's GENERIC
+build).  What is exercised is everything between the C ABI and the kernel launch: argument
+normalisation, pointer classification, packing / strided copies / pinned slot rings, the panel
+pipeline, batch staging, the dispatcher's fallbacks, the block-column and masked-triangle schemes of
+the SYRK family, the TRMM / TRSM recursion and its operand offsets.  The real kernels are covered by
+the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+import level3_helpers as L
+from helpers import ALL_DTYPES, NAMES, alpha_beta, ntrans, problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    out = subprocess.check_output([os.path.join(ROOT, "tests", "hostsim", "build.sh")], text=True).strip().splitlines()[-1]
+    lib = C.CDLL(out)
+    lib.b200_last_kernel.restype = C.c_char_p
+    lib.b200_launch_count.restype = C.c_uint64
+    lib.hostsim_copy_count.restype = C.c_size_t
+    lib.hostsim_device_alloc.restype = C.c_void_p
+    lib.hostsim_device_alloc.argtypes = [C.c_size_t]
+    lib.hostsim_pinned_alloc.restype = C.c_void_p
+    lib.hostsim_pinned_alloc.argtypes = [C.c_size_t]
+    lib.hostsim_free.argtypes = [C.c_void_p]
+    return lib
+
+
+def fgemm(lib, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+    fn = getattr(lib, cpu.DTYPE_NAMES[dtype] + "gemm_")
+    al, be = cpu.scalar_bytes(dtype, alpha), cpu.scalar_bytes(dtype, beta)
+    i = lambda v: C.byref(C.c_int(int(v)))
+    P = lambda x: C.c_void_p(x) if isinstance(x, int) else x.ctypes.data_as(C.c_void_p)      # a bare int would be passed as a 32-bit int
+    fn(C.c_char_p(cpu.TRANS_CHAR[ta].encode()), C.c_char_p(cpu.TRANS_CHAR[tb].encode()), i(m), i(n), i(k), cpu._ptr(al), P(a), i(lda),
+       P(b), i(ldb), cpu._ptr(be), P(c), i(ldc))
+
+
+def test_gemm_golden_vectors_bitwise_through_the_host_path(sim, golden):
+    """All 88 reference-generated GEMM cases: host path + oracle must reproduce the REFERENCE's bytes."""
+    for idx, row in enumerate(golden["meta"]):
+        dtype, ta, tb, m, n, k, lda, ldb, ldc = (int(v) for v in row[:9])
+        cplx = dtype in (cpu.CX, cpu.Z)
+        alpha = complex(row[9], row[10]) if cplx else row[9]
+        beta = complex(row[11], row[12]) if cplx else row[11]
+        got = golden[f"c0_{idx}"].copy()
+        fgemm(sim, dtype, ta, tb, m, n, k, alpha, golden[f"a{idx}"], lda, golden[f"b{idx}"], ldb, beta, got, ldc)
+        assert np.array_equal(got.view(np.uint8), golden[f"c{idx}"].view(np.uint8)), (idx, NAMES[dtype], ta, tb, m, n, k)
+
+
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.Z, cpu.S, cpu.SB])
+def test_every_staging_path_equals_the_oracle_bitwise(sim, oracle, dtype):
+    """Small (one packed block), middle (strided copies, pinned slot ring for pageable memory) and
+    pipelined (A row panels / B column panels / C blocks) host paths, every op combination, beta == 0
+    over NaN and beta != 0, pageable, pinned and device operands.  Each element's k order is the same
+    whatever the blocking of m and n, so the result must equal one oracle call on the whole problem."""
+    rng = np.random.default_rng(40 + dtype)
+    es_out = np.dtype(cpu.NP_OUT[dtype]).itemsize
+    shapes = [(9, 7, 5), (70, 50, 33), (150, 130, 40), (300, 280, 12)]
+    seen_multi = False
+    for (m, n, k) in shapes:
+        for ta in range(ntrans(dtype)):
+            for tb in range(ntrans(dtype)):
+                for beta_zero in (False, True):
+                    a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(1, 2, 3))
+                    alpha, beta = alpha_beta(dtype)[0][2], (0.0 if beta_zero else alpha_beta(dtype)[1][2])
+                    if beta_zero:
+                        c0[:, :m] = np.nan
+                    want = c0.copy()
+                    oracle.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, want, ldc)
+                    before = sim.b200_launch_count()
+                    got = c0.copy()
+                    fgemm(sim, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, got, ldc)
+                    seen_multi |= sim.b200_launch_count() - before > 1
+                    assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (NAMES[dtype], ta, tb, m, n, k, beta_zero)
+    assert seen_multi, "the panel pipeline (several block GEMMs per call) was never taken"
+    # pinned and device operands: same answers
+    m, n, k = 150, 130, 40
+    a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 0, 1, m, n, k, pad=(0, 0, 0))
+    alpha, beta = alpha_beta(dtype)[0][2], alpha_beta(dtype)[1][2]
+    want = c0.copy()
+    oracle.gemm(dtype, 0, 1, m, n, k, alpha, a, lda, b, ldb, beta, want, ldc)
+    for alloc in (sim.hostsim_pinned_alloc, sim.hostsim_device_alloc):
+        bufs = []
+        for x in (a, b, c0):
+            p = alloc(x.nbytes)
+            C.memmove(p, x.ctypes.data, x.nbytes)
+            bufs.append(p)
+        fgemm(sim, dtype, 0, 1, m, n, k, alpha, bufs[0], lda, bufs[1], ldb, beta, bufs[2], ldc)
+        got = np.empty_like(c0)
+        C.memmove(got.ctypes.data, bufs[2], got.nbytes)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), alloc
+        for p in bufs:
+            sim.hostsim_free(p)
+    assert es_out in (4, 8, 16)
+
+
+def test_gemm_batch_is_staged_in_one_upload_and_one_download(sim, oracle):
+    rng = np.random.default_rng(9)
+    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2), (0, 0, 30, 20, 16, 4), (1, 1, 7, 5, 3, 4)]
+    alphas, betas = [0.7, 1.0, -0.4, 2.0], [1.3, 0.0, 1.0, 0.0]
+    cb = {0: 111, 1: 112}
+    probs = []
+    for gi, (ta, tb, m, n, k, cnt) in enumerate(groups):
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, ta, tb, m, n, k, pad=(1, 1, 1))
+            got = c0.copy()
+            if betas[gi] == 0.0:
+                got[:, :m] = np.nan
+            probs.append((a, lda, b, ldb, c0, got, ldc))
+    ints = lambda v: (C.c_int * len(v))(*v)
+    first = [sum(g[5] for g in groups[:i]) for i in range(len(groups))]
+    ptrs = lambda j: (C.c_void_p * len(probs))(*[p[j].ctypes.data for p in probs])
+    copies, launches = sim.hostsim_copy_count(), sim.b200_launch_count()
+    sim.cblas_dgemm_batch(102, ints([cb[g[0]] for g in groups]), ints([cb[g[1]] for g in groups]), ints([g[2] for g in groups]),
+                          ints([g[3] for g in groups]), ints([g[4] for g in groups]), (C.c_double * 4)(*alphas), ptrs(0),
+                          ints([probs[f][1] for f in first]), ptrs(2), ints([probs[f][3] for f in first]), (C.c_double * 4)(*betas),
+                          ptrs(5), ints([probs[f][6] for f in first]), len(groups), ints([g[5] for g in groups]))
+    assert sim.hostsim_copy_count() - copies == 2, "a packed batch is one H2D and one D2H"
+    assert sim.b200_launch_count() - launches == len(probs)
+    i = 0
+    for gi, (ta, tb, m, n, k, cnt) in enumerate(groups):
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, got, ldc = probs[i]
+            i += 1
+            want = c0.copy()
+            oracle.gemm(cpu.D, ta, tb, m, n, k, alphas[gi], a, lda, b, ldb, betas[gi], want, ldc)
+            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (gi, m, n, k)
+
+
+def test_level3_family_golden_vectors_through_the_host_path(sim, oracle):
+    """The 144 + 192 reference-generated cases of SYMM/HEMM/SYRK/HERK/SYR2K/HER2K and TRMM/TRSM: operand
+    expansion, block columns, triangle merge, recursion order and offsets, with the oracle as GEMM."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "level3_golden.npz"))
+    call = L.bind(sim)
+    for idx, row in enumerate(g["meta"]):
+        case = L.meta_case(row)
+        a, b, c0, ref_c = g[f"a{idx}"], g[f"b{idx}"], g[f"c0_{idx}"], g[f"c{idx}"]
+        got, _, gauge, K, touched = L.run_case(call, oracle, case, a, b if b.size else a, c0)
+        L.check_case(case, got, ref_c, gauge, K, touched, c0)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trxm_golden.npz"))
+    for idx, row in enumerate(g["meta"]):
+        L.check_trxm(oracle, sim, L.trxm_meta_case(row), g[f"a{idx}"], g[f"b0_{idx}"])
+
+
+@pytest.mark.parametrize("rankk_tri", ["1", "0"])
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.CX])
+def test_rank_k_schemes_and_symm_at_block_crossing_sizes(sim, oracle, dtype, rankk_tri, monkeypatch):
+    """n = 300 crosses the 128-wide block columns of the fallback scheme; B200_RANKK_TRI selects it or
+    the masked-triangle GEMM.  NaN fills whatever must not be read or written."""
+    monkeypatch.setenv("B200_RANKK_TRI", rankk_tri)
+    call = L.bind(sim)
+    rng = np.random.default_rng(300 + dtype)
+    cplx = dtype in (cpu.CX, cpu.Z)
+    for herm in ((0, 1) if cplx else (0,)):
+        for x in (0, 1):
+            for uplo in (0, 1):
+                m, n = 90, 70
+                ka = n if x else m
+                a, b, c0 = L.operand(rng, dtype, ka, ka + 1), L.operand(rng, dtype, n, m + 2), L.operand(rng, dtype, n, m + 3)
+                jj, ii = np.meshgrid(np.arange(ka), np.arange(ka + 1), indexing="ij")
+                a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
+                alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
+                case = (0, dtype, herm, x, uplo, 0, m, n, 0, ka + 1, m + 2, m + 3, alpha, beta)
+                got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+                L.check_case(case, got, want, gauge, K, touched, c0)
+                for trans in (0, 1):
+                    for (nn, k, beta_zero) in [(300, 24, False), (140, 33, True)]:
+                        rows, cols = (k, nn) if trans else (nn, k)
+                        a, b = L.operand(rng, dtype, cols, rows + 2), L.operand(rng, dtype, cols, rows + 4)
+                        c0 = L.operand(rng, dtype, nn, nn + 3)
+                        jj, ii = np.meshgrid(np.arange(nn), np.arange(nn + 3), indexing="ij")
+                        if beta_zero:
+                            c0[:, :nn] = np.nan
+                        else:
+                            c0[((ii < jj) if uplo else (ii > jj)) & (ii < nn)] = np.nan
+                        al = 0.7 if (herm and not x) or not cplx else 0.7 - 0.9j
+                        be = 0.0 if beta_zero else (1.3 if herm or not cplx else 1.3 - 1.1j)
+                        case = (1, dtype, herm, x, uplo, trans, nn, nn, k, rows + 2, rows + 4, nn + 3, al, be)
+                        got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+                        L.check_case(case, got, want, gauge, K, touched, c0)
+                        if nn == 300:
+                            assert (sim.b200_last_kernel() == b"sim_tri_merge") == (rankk_tri == "0"), sim.b200_last_kernel()
+
+
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.Z])
+def test_trxm_recursion_offsets(sim, oracle, dtype):
+    """Triangles of 150 and 203 rows (three / four levels of the recursive split, ragged last block),
+    every side / uplo / trans / diag combination, through the real recursion with simulated kernels."""
+    rng = np.random.default_rng(900 + dtype)
+    cplx = dtype in (cpu.CX, cpu.Z)
+    alpha = (0.7 - 0.9j) if cplx else 0.7
+    for solve in (0, 1):
+        for side in (0, 1):
+            for uplo in (0, 1):
+                for trans in range(4 if cplx else 2):
+                    for unit in (0, 1):
+                        m, n = (150, 20) if (trans + unit) % 2 == 0 else (17, 203)
+                        ka = n if side else m
+                        a = L.tri_operand(rng, dtype, ka, ka + 1, uplo, unit)
+                        if solve:
+                            off = ~np.eye(ka, ka + 1, dtype=bool)
+                            a[off] *= 4.0 / ka
+                        b0 = L.operand(rng, dtype, n, m + 2)
+                        L.check_trxm(oracle, sim, (dtype, solve, side, uplo, trans, unit, m, n, ka + 1, m + 2, alpha), a, b0)
+
+
+def test_row_major_cblas_entry_points(sim):
+    """Row-major normalisation of every family against numpy on the logical matrices."""
+    rng = np.random.default_rng(5)
+    m, n, k = 23, 17, 29
+    A, B, Cm = rng.random((m, k)) - 0.5, rng.random((k, n)) - 0.5, rng.random((m, n)) - 0.5
+    got = Cm.copy()
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    sim.cblas_dgemm(101, 111, 111, m, n, k, C.c_double(0.7), P(A), k, P(B), n, C.c_double(1.3), P(got), n)
+    assert np.allclose(got, 0.7 * A @ B + 1.3 * Cm, rtol=0, atol=1e-13)
+    At = np.ascontiguousarray(A.T)      # k x m row-major, used transposed
+    got = Cm.copy()
+    sim.cblas_dgemm(101, 112, 111, m, n, k, C.c_double(0.7), P(At), m, P(B), n, C.c_double(0.0), P(got), n)
+    assert np.allclose(got, 0.7 * A @ B, rtol=0, atol=1e-13)
+    # ZHER2K row-major upper, NoTrans: conj(alpha) handling of interface/syr2k.c:305-311
+    nn, kk = 21, 13
+    Az = rng.random((nn, kk)) - 0.5 + 1j * (rng.random((nn, kk)) - 0.5)
+    Bz = rng.random((nn, kk)) - 0.5 + 1j * (rng.random((nn, kk)) - 0.5)
+    C0 = rng.random((nn, nn)) - 0.5 + 1j * (rng.random((nn, nn)) - 0.5)
+    alpha = 0.7 - 0.9j
+    got = C0.copy()
+    al = np.array([alpha.real, alpha.imag])
+    sim.cblas_zher2k(101, 121, 111, nn, kk, P(al), P(Az), kk, P(Bz), kk, C.c_double(1.3), P(got), nn)
+    full = alpha * Az @ Bz.conj().T + np.conj(alpha) * Bz @ Az.conj().T + 1.3 * C0
+    up = np.triu(np.ones((nn, nn), dtype=bool))
+    assert np.allclose(got[up], np.where(np.eye(nn, dtype=bool), full.real + 0j, full)[up], rtol=0, atol=1e-13)
+    assert np.array_equal(got[~up], C0[~up])
+    # DTRSM row-major, Right, Lower, Trans, NonUnit: X * L^T = alpha * B
+    Lm = np.tril(rng.random((n, n)) - 0.5) * 0.2 + np.eye(n)
+    Bm = rng.random((m, n)) - 0.5
+    X = Bm.copy()
+    sim.cblas_dtrsm(101, 142, 122, 112, 131, m, n, C.c_double(0.7), P(Lm), n, P(X), n)
+    assert np.allclose(X @ Lm.T, 0.7 * Bm, rtol=0, atol=1e-12)
+    # DSYMM row-major, Left, Upper
+    S = rng.random((m, m)) - 0.5
+    S = np.triu(S) + np.triu(S, 1).T
+    Su = np.triu(S) + np.tril(np.full((m, m), np.nan), -1)
+    Bs = rng.random((m, n)) - 0.5
+    got = Cm.copy()
+    sim.cblas_dsymm(101, 141, 121, m, n, C.c_double(0.7), P(Su), m, P(Bs), n, C.c_double(1.3), P(got), n)
+    assert np.allclose(got, 0.7 * S @ Bs + 1.3 * Cm, rtol=0, atol=1e-13)
+
+
+def test_bf16_conversions_through_the_host_path(sim):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bf16_golden.npz"))
+    x = g["x"]
+    h = np.zeros(x.size, dtype=np.uint16)
+    sim.cblas_sbstobf16(x.size, x.ctypes.data_as(C.c_void_p), 1, h.ctypes.data_as(C.c_void_p), 1)
+    assert np.array_equal(h, g["bf16"])
+    h2 = np.full(2 * 50, 0xdead, dtype=np.uint16)
+    sim.cblas_sbstobf16(50, x.ctypes.data_as(C.c_void_p), 1, h2.ctypes.data_as(C.c_void_p), -2)
+    assert np.array_equal(h2[::2][::-1], g["bf16"][:50]) and np.all(h2[1::2] == 0xdead)
