@@ -94,7 +94,7 @@ def test_summa_gloo_matches_oracle(world, shape):
     directions, ranks that own no block of a short dimension, ragged last blocks."""
     m, n, k, nb = shape
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # never fork this (by now multi-threaded) test process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, m, n, k, nb, out), nprocs=world, join=True)
     assert len(out) == world
