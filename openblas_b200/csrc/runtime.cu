@@ -55,7 +55,7 @@ namespace b200 {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_forced_kernel{B200_K_AUTO};
 static std::mutex g_mu;
-static int g_device = -1;
+static std::atomic<int> g_device{-1};   /* published last (release) by ensure_init; g_sm_count and g_init_pid are read after an acquire load of it */
 static int g_sm_count = 0;
 static pid_t g_init_pid = 0;
 
@@ -99,7 +99,7 @@ struct Context {
 static std::vector<Context *> g_free_ctx;
 
 static int ensure_init() {
-  if (g_device >= 0) {
+  if (g_device.load(std::memory_order_acquire) >= 0) {
     if (getpid() != g_init_pid) {
       snprintf(t_error, sizeof t_error,
                "the CUDA context was created in parent process %d and cannot be used after fork() "
@@ -110,7 +110,7 @@ static int ensure_init() {
     return 0;
   }
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_device >= 0) return 0;
+  if (g_device.load(std::memory_order_acquire) >= 0) return 0;
   int dev = 0, count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -129,7 +129,7 @@ static int ensure_init() {
   }
   g_sm_count = prop.multiProcessorCount;
   g_init_pid = getpid();
-  g_device = dev;
+  g_device.store(dev, std::memory_order_release);
   return 0;
 }
 
@@ -140,7 +140,7 @@ static int acquire(Context **out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_free_ctx.empty()) { *out = g_free_ctx.back(); g_free_ctx.pop_back(); return 0; }
   }
-  CK(cudaSetDevice(g_device));
+  CK(cudaSetDevice(g_device.load(std::memory_order_acquire)));
   Context *c = new Context();
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   *out = c;
@@ -821,7 +821,7 @@ B200_EXPORT const char *b200_last_error(void) { return t_error; }
 B200_EXPORT const char *b200_version(void) { return "openblas_b200 0.1 (sm_100a; ABI of OpenBLAS 0.3.28.dev)"; }
 
 B200_EXPORT int b200_init(int device) {
-  if (g_device < 0) {
+  if (g_device.load(std::memory_order_acquire) < 0) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return set_error(e, "cudaSetDevice");
   }

@@ -6,17 +6,18 @@
 # is already loaded in the process (torch).
 set -e
 ROOT="$(cd "$(dirname "$0")/../.." && pwd)"
-OUT="$ROOT/tests/_build"
+OUT="$ROOT/tests/_build${HOSTSIM_SANITIZE:+/$HOSTSIM_SANITIZE}"
+SAN="${HOSTSIM_SANITIZE:+-fsanitize=$HOSTSIM_SANITIZE -fno-omit-frame-pointer}"      # HOSTSIM_SANITIZE=address|thread: instrumented build
 mkdir -p "$OUT"
 make -s -C "$ROOT/oracle" _build/liboracle.so
 CSRC="$ROOT/openblas_b200/csrc"
 INC="-I/usr/local/cuda/include -I$CSRC -I$ROOT/include"
-g++ -std=c++17 -O1 -g -fPIC -fvisibility=hidden -DB200_HOSTSIM $INC -x c++ -c "$CSRC/runtime.cu" -o "$OUT/runtime.o"
-g++ -std=c++17 -O1 -g -fPIC -fvisibility=hidden -DB200_HOSTSIM $INC -c "$ROOT/tests/hostsim/sim_kernels.cpp" -o "$OUT/sim_kernels.o"
-g++ -std=c++17 -O1 -g -fPIC -DB200_HOSTSIM $INC -c "$ROOT/tests/hostsim/cuda_shim.cpp" -o "$OUT/cuda_shim.o"
+g++ $SAN -std=c++17 -O1 -g -fPIC -fvisibility=hidden -DB200_HOSTSIM $INC -x c++ -c "$CSRC/runtime.cu" -o "$OUT/runtime.o"
+g++ $SAN -std=c++17 -O1 -g -fPIC -fvisibility=hidden -DB200_HOSTSIM $INC -c "$ROOT/tests/hostsim/sim_kernels.cpp" -o "$OUT/sim_kernels.o"
+g++ $SAN -std=c++17 -O1 -g -fPIC -DB200_HOSTSIM $INC -c "$ROOT/tests/hostsim/cuda_shim.cpp" -o "$OUT/cuda_shim.o"
 for f in interface_gemm interface_level3 xerbla control; do
-  gcc -O1 -g -fPIC -fvisibility=hidden -std=gnu11 $INC -c "$CSRC/$f.c" -o "$OUT/$f.o"
+  gcc $SAN -O1 -g -fPIC -fvisibility=hidden -std=gnu11 $INC -c "$CSRC/$f.c" -o "$OUT/$f.o"
 done
-g++ -shared -o "$OUT/libopenblas_b200_hostsim.so" "$OUT"/runtime.o "$OUT"/sim_kernels.o "$OUT"/cuda_shim.o "$OUT"/interface_gemm.o \
+g++ $SAN -shared -o "$OUT/libopenblas_b200_hostsim.so" "$OUT"/runtime.o "$OUT"/sim_kernels.o "$OUT"/cuda_shim.o "$OUT"/interface_gemm.o \
     "$OUT"/interface_level3.o "$OUT"/xerbla.o "$OUT"/control.o -Wl,-Bsymbolic -L"$ROOT/oracle/_build" -loracle -Wl,-rpath,"$ROOT/oracle/_build" -lpthread
 echo "$OUT/libopenblas_b200_hostsim.so"

@@ -14,13 +14,15 @@
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
 
 namespace {
 std::mutex g_mu;
 std::map<const char *, std::pair<size_t, int>> g_blocks;   /* base -> (bytes, 1 device / 2 pinned) */
-size_t g_device_bytes = 0, g_copies = 0;
+size_t g_device_bytes = 0;
+std::atomic<size_t> g_copies{0};
 
 void *alloc_block(size_t n, int kind) {
   if (n == 0) n = 1;
@@ -94,6 +96,6 @@ cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 __attribute__((visibility("default"))) void *hostsim_device_alloc(size_t n) { return alloc_block(n, 1); }
 __attribute__((visibility("default"))) void *hostsim_pinned_alloc(size_t n) { return alloc_block(n, 2); }
 __attribute__((visibility("default"))) void hostsim_free(void *p) { free_block(p); }
-__attribute__((visibility("default"))) size_t hostsim_copy_count(void) { return g_copies; }
+__attribute__((visibility("default"))) size_t hostsim_copy_count(void) { return g_copies.load(); }
 
 }  // extern "C"
