@@ -293,3 +293,94 @@ def test_concurrent_callers_identical_and_race_free():
     assert r.returncode == 0, r.stdout[-3000:]
     assert "THREADS OK" in r.stdout, r.stdout[-3000:]
     assert "WARNING: ThreadSanitizer" not in r.stdout, r.stdout[-6000:]
+
+
+def test_extension_api_and_kernel_forcing(sim, oracle):
+    """Part 2 of the header: b200_gemm on host / pinned / device pointers, b200_gemm_async on device
+    pointers, b200_set_kernel: GENERIC always works, FAST reports cudaErrorNotSupported (801) for a
+    problem the roofline kernels do not take instead of silently running something else."""
+    sim.b200_gemm.restype = C.c_int
+    sim.b200_gemm_async.restype = C.c_int
+    sim.b200_host_alloc.restype = C.c_void_p
+    sim.b200_host_alloc.argtypes = [C.c_size_t]
+    sim.b200_host_free.argtypes = [C.c_void_p]
+    sim.b200_last_error.restype = C.c_char_p
+    rng = np.random.default_rng(2)
+    m, n, k = 96, 80, 64
+    a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, 0, 0, m, n, k, pad=(0, 0, 0))
+    want = c0.copy()
+    oracle.gemm(cpu.D, 0, 0, m, n, k, 0.7, a, lda, b, ldb, 1.3, want, ldc)
+    al, be = np.array([0.7]), np.array([1.3])
+    i64 = C.c_int64
+    P = lambda x: C.c_void_p(x) if isinstance(x, int) else x.ctypes.data_as(C.c_void_p)
+    args = lambda pa, pb, pc: (1, 0, 0, i64(m), i64(n), i64(k), P(al), P(pa), i64(lda), P(pb), i64(ldb), P(be), P(pc), i64(ldc))
+    got = c0.copy()
+    assert sim.b200_gemm(*args(a, b, got)) == 0
+    assert np.array_equal(got, want)      # (host operands of this size take the panel pipeline: 32 x 32 blocks -> generic kernel)
+    # pinned memory from the library's own allocator, then device memory through the async entry point
+    for alloc, free, use_async in ((sim.b200_host_alloc, sim.b200_host_free, False), (sim.hostsim_device_alloc, sim.hostsim_free, True)):
+        bufs = []
+        for x in (a, b, c0):
+            p = alloc(x.nbytes)
+            C.memmove(p, x.ctypes.data, x.nbytes)
+            bufs.append(p)
+        if use_async:
+            assert sim.b200_gemm_async(*args(*bufs), None) == 0
+        else:
+            assert sim.b200_gemm(*args(*bufs)) == 0
+        got = np.empty_like(c0)
+        C.memmove(got.ctypes.data, bufs[2], got.nbytes)
+        assert np.array_equal(got, want)
+        if use_async:                   # device operands are used in place: one launch of the roofline kernel's stand-in
+            assert sim.b200_last_kernel().startswith(b"sim_dgemm"), sim.b200_last_kernel()
+        for p in bufs:
+            free(p)
+    try:
+        sim.b200_set_kernel(1)                       # GENERIC
+        got = c0.copy()
+        dev = []
+        for x in (a, b, c0):
+            p = sim.hostsim_device_alloc(x.nbytes)
+            C.memmove(p, x.ctypes.data, x.nbytes)
+            dev.append(p)
+        assert sim.b200_gemm(*args(*dev)) == 0 and sim.b200_last_kernel() == b"sim_generic"
+        C.memmove(got.ctypes.data, dev[2], got.nbytes)
+        assert np.array_equal(got, want)
+        for p in dev:
+            sim.hostsim_free(p)
+        sim.b200_set_kernel(2)                       # FAST: an SBGEMM the tcgen05 kernel refuses (m < 128)
+        assert sim.b200_get_kernel() == 2
+        ha, hb = oracle.tobf16(rng.random((k, m), dtype=np.float32)), oracle.tobf16(rng.random((n, k), dtype=np.float32))
+        hc = np.zeros((n, m), dtype=np.float32)
+        fa, fb = np.array([1.0], dtype=np.float32), np.array([0.0], dtype=np.float32)
+        rc = sim.b200_gemm(4, 0, 0, i64(m), i64(n), i64(k), P(fa), P(ha), i64(m), P(hb), i64(k), P(fb), P(hc), i64(m))
+        assert rc == 801, rc
+    finally:
+        sim.b200_set_kernel(0)
+
+
+def test_fork_after_first_use_fails_loudly(tmp_path):
+    """DESIGN 'known deviations': the CUDA context does not survive fork(); a GEMM in a child forked
+    after the parent's first call must abort with an explanation, not compute on a dead context."""
+    lib = subprocess.check_output([os.path.join(ROOT, "tests", "hostsim", "build.sh")], text=True).strip().splitlines()[-1]
+    script = tmp_path / "fork_child.py"
+    script.write_text(f'''
+import ctypes as C, os, sys
+import numpy as np
+lib = C.CDLL({lib!r})
+a = np.ones((64, 64)); c = np.zeros((64, 64))
+def call():
+    lib.cblas_dgemm(102, 111, 111, 64, 64, 64, C.c_double(1.0), a.ctypes.data_as(C.c_void_p), 64, a.ctypes.data_as(C.c_void_p), 64,
+                    C.c_double(0.0), c.ctypes.data_as(C.c_void_p), 64)
+call()
+assert c[0, 0] == 64.0
+pid = os.fork()
+if pid == 0:
+    call()
+    os._exit(0)
+_, status = os.waitpid(pid, 0)
+print("child signal", os.WTERMSIG(status) if os.WIFSIGNALED(status) else 0, "exit", os.WEXITSTATUS(status) if os.WIFEXITED(status) else -1)
+''')
+    r = subprocess.run(["python", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert "child signal 6" in r.stdout, r.stdout            # SIGABRT from b200_fatal
+    assert "cannot be used after fork()" in r.stdout, r.stdout
