@@ -647,8 +647,9 @@ B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
 /* gemm_batch (interface/gemm_batch.c:322-366 hands one queue entry per matrix to the thread pool):
  * when every operand lives in host memory and the whole batch packs into 64 MB, all A and B
  * blocks go up in ONE copy, every matrix gets its own kernel launch on one stream, and all C
- * blocks come back in ONE copy -- one synchronisation per batch instead of one per matrix.
- * Anything else (device operands, huge matrices) runs matrix by matrix. */
+ * blocks come back in ONE copy -- one synchronisation per batch instead of one per matrix.  A batch
+ * whose operands are all device memory is launched back to back and synchronised once.  Anything
+ * else (mixed host / device operands, huge matrices) runs matrix by matrix. */
 static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, bool *handled) {
   *handled = false;
   static const bool enabled = !(getenv("B200_BATCH_PACKED") && atoi(getenv("B200_BATCH_PACKED")) == 0);
@@ -657,6 +658,33 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
   std::vector<Item> items((size_t)count);
   size_t ab_bytes = 0, c_bytes = 0;
   bool any_beta = false;
+
+  /* every operand already on the device: no staging at all -- wait once for whatever the caller has in
+   * flight, launch every matrix on one stream, synchronise once */
+  {
+    bool all_device = true;
+    for (int64_t i = 0; i < count && all_device; i++) {
+      DeviceGemm g;
+      read_scalars(&p[i], g);
+      const bool product = p[i].k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
+      all_device = classify(p[i].c) == PTR_DEVICE && (!product || (classify(p[i].a) == PTR_DEVICE && classify(p[i].b) == PTR_DEVICE));
+    }
+    if (all_device) {
+      CK(cudaDeviceSynchronize());
+      for (int64_t i = 0; i < count; i++) {
+        const b200_problem &q = p[i];
+        DeviceGemm g;
+        g.dtype = q.dtype; g.transa = q.transa; g.transb = q.transb; g.m = q.m; g.n = q.n; g.k = q.k;
+        g.a = q.a; g.b = q.b; g.c = q.c; g.lda = q.lda; g.ldb = q.ldb; g.ldc = q.ldc;
+        read_scalars(&q, g);
+        CK(dispatch(g, ctx->stream));
+      }
+      CK(cudaStreamSynchronize(ctx->stream));
+      *handled = true;
+      return 0;
+    }
+  }
+
   for (int64_t i = 0; i < count; i++) {
     Item &it = items[(size_t)i];
     const b200_problem &q = p[i];

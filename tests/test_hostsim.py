@@ -384,3 +384,32 @@ print("child signal", os.WTERMSIG(status) if os.WIFSIGNALED(status) else 0, "exi
     r = subprocess.run(["python", str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert "child signal 6" in r.stdout, r.stdout            # SIGABRT from b200_fatal
     assert "cannot be used after fork()" in r.stdout, r.stdout
+
+
+def test_gemm_batch_on_device_operands_needs_no_copies(sim, oracle):
+    rng = np.random.default_rng(21)
+    m, n, k, cnt = 48, 40, 36, 5
+    hosts, devs = [], []
+    for _ in range(cnt):
+        a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, 0, 1, m, n, k, pad=(2, 2, 2))
+        ptrs = []
+        for x in (a, b, c0):
+            p = sim.hostsim_device_alloc(x.nbytes)
+            C.memmove(p, x.ctypes.data, x.nbytes)
+            ptrs.append(p)
+        hosts.append((a, lda, b, ldb, c0, ldc))
+        devs.append(ptrs)
+    ints = lambda v: (C.c_int * len(v))(*v)
+    vp = lambda j: (C.c_void_p * cnt)(*[d[j] for d in devs])
+    copies, launches = sim.hostsim_copy_count(), sim.b200_launch_count()
+    sim.cblas_dgemm_batch(102, ints([111]), ints([112]), ints([m]), ints([n]), ints([k]), (C.c_double * 1)(0.7), vp(0), ints([hosts[0][1]]),
+                          vp(1), ints([hosts[0][3]]), (C.c_double * 1)(1.3), vp(2), ints([hosts[0][5]]), 1, ints([cnt]))
+    assert sim.hostsim_copy_count() == copies and sim.b200_launch_count() - launches == cnt
+    for (a, lda, b, ldb, c0, ldc), d in zip(hosts, devs):
+        want = c0.copy()
+        oracle.gemm(cpu.D, 0, 1, m, n, k, 0.7, a, lda, b, ldb, 1.3, want, ldc)
+        got = np.empty_like(c0)
+        C.memmove(got.ctypes.data, d[2], got.nbytes)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+        for p in d:
+            sim.hostsim_free(p)
