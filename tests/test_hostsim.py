@@ -413,3 +413,108 @@ def test_gemm_batch_on_device_operands_needs_no_copies(sim, oracle):
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
         for p in d:
             sim.hostsim_free(p)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_randomised_gemm_staging_stress(sim, oracle, seed):
+    """Random GEMMs around every threshold of the host path: extents from sets that straddle the packed /
+    strided / pipelined limits and the panel edges (0 included), random leading-dimension padding,
+    alpha and beta from {0, 1, other}, every operand independently pageable, pinned or device memory,
+    all five precisions.  Result = one oracle call, bit for bit; padding rows keep their bytes."""
+    rng = np.random.default_rng(1000 + seed)
+    dims = [0, 1, 2, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 200, 257]
+    ks = [0, 1, 5, 33, 64]
+    allocs = [None, sim.hostsim_pinned_alloc, sim.hostsim_device_alloc]
+    for it in range(60):
+        dtype = int(rng.integers(0, 5))
+        m, n, k = int(rng.choice(dims)), int(rng.choice(dims)), int(rng.choice(ks))
+        if m * n * max(k, 1) > 3_000_000:
+            k = min(k, 5)
+        ta, tb = int(rng.integers(0, ntrans(dtype))), int(rng.integers(0, ntrans(dtype)))
+        pad = tuple(int(x) for x in rng.integers(0, 4, size=3))
+        a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=pad)
+        alphas, betas = alpha_beta(dtype)
+        alpha, beta = alphas[int(rng.integers(0, 3))], betas[int(rng.integers(0, 3))]
+        if complex(beta) == 0:
+            c0[:, :m] = np.nan
+        want = c0.copy()
+        oracle.gemm(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, want, ldc)
+        kinds = [allocs[int(rng.integers(0, 3))] for _ in range(3)]
+        ptrs, owned = [], []
+        for x, alloc in zip((a, b, c0.copy()), kinds):
+            if alloc is None:
+                ptrs.append(x)
+            else:
+                p = alloc(max(x.nbytes, 1))
+                C.memmove(p, x.ctypes.data, x.nbytes)
+                ptrs.append(p)
+                owned.append(p)
+        fgemm(sim, dtype, ta, tb, m, n, k, alpha, ptrs[0], lda, ptrs[1], ldb, beta, ptrs[2], ldc)
+        if isinstance(ptrs[2], int):
+            got = np.empty_like(c0)
+            C.memmove(got.ctypes.data, ptrs[2], got.nbytes)
+        else:
+            got = ptrs[2]
+        ctx = (seed, it, NAMES[dtype], ta, tb, m, n, k, pad, alpha, beta, [k_ is not None and k_ is sim.hostsim_device_alloc for k_ in kinds])
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), ctx
+        for p in owned:
+            sim.hostsim_free(p)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_randomised_level3_stress(sim, oracle, seed, monkeypatch):
+    """Random SYMM/HEMM, SYRK/HERK, SYR2K/HER2K, TRMM/TRSM calls: extents around the 64-wide recursion
+    blocks and the 128-wide block columns (1 included), alpha / beta from {0, 1, other}, both rank-k
+    schemes, against the oracle within the level-3 bounds, untouched parts bit-identical."""
+    rng = np.random.default_rng(2000 + seed)
+    call = L.bind(sim)
+    dims = [1, 2, 31, 63, 64, 65, 127, 128, 129, 200]
+    for it in range(40):
+        monkeypatch.setenv("B200_RANKK_TRI", str(int(rng.integers(0, 2))))
+        dtype = int(rng.integers(0, 4))
+        cplx = dtype in (cpu.CX, cpu.Z)
+        fam = int(rng.integers(0, 3))
+        m, n, k = int(rng.choice(dims)), int(rng.choice(dims)), int(rng.choice([0, 1, 7, 40]))
+        scal = [0.0, 1.0, (0.7 - 0.9j) if cplx else 0.7]
+        alpha, beta = scal[int(rng.integers(0, 3))], scal[int(rng.integers(0, 3))]
+        uplo = int(rng.integers(0, 2))
+        if fam == 0:
+            herm, side = (int(rng.integers(0, 2)) if cplx else 0), int(rng.integers(0, 2))
+            ka = n if side else m
+            pa, pb, pc = (int(x) for x in rng.integers(0, 3, size=3))
+            a, b, c0 = L.operand(rng, dtype, ka, ka + pa), L.operand(rng, dtype, n, m + pb), L.operand(rng, dtype, n, m + pc)
+            jj, ii = np.meshgrid(np.arange(ka), np.arange(ka + pa), indexing="ij")
+            a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
+            if complex(beta) == 0:
+                c0[:, :m] = np.nan
+            case = (0, dtype, herm, side, uplo, 0, m, n, 0, ka + pa, m + pb, m + pc, alpha, beta)
+            got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+            L.check_case(case, got, want, gauge, K, touched, c0)
+        elif fam == 1:
+            herm, two, trans = (int(rng.integers(0, 2)) if cplx else 0), int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            rows, cols = (k, n) if trans else (n, k)
+            pa, pb, pc = (int(x) for x in rng.integers(0, 3, size=3))
+            a, b = L.operand(rng, dtype, max(cols, 1), max(rows, 1) + pa), L.operand(rng, dtype, max(cols, 1), max(rows, 1) + pb)
+            c0 = L.operand(rng, dtype, n, n + pc)
+            al = complex(alpha).real if (herm and not two) else alpha
+            be = complex(beta).real if herm else beta
+            jj, ii = np.meshgrid(np.arange(n), np.arange(n + pc), indexing="ij")
+            if complex(be) == 0:
+                c0[:, :n] = np.nan
+            else:
+                c0[((ii < jj) if uplo else (ii > jj)) & (ii < n)] = np.nan
+            case = (1, dtype, herm, two, uplo, trans, n, n, k, max(rows, 1) + pa, max(rows, 1) + pb, n + pc, al, be)
+            got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+            if complex(be) == 1 and (k == 0 or complex(al) == 0):
+                assert np.array_equal(got.view(np.uint8), c0.view(np.uint8))
+            else:
+                L.check_case(case, got, want, gauge, K, touched, c0)
+        else:
+            solve, side, trans, unit = int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 4 if cplx else 2)), int(rng.integers(0, 2))
+            ka = n if side else m
+            a = L.tri_operand(rng, dtype, ka, ka + 1, uplo, unit)
+            if solve and ka > 1:
+                off = ~np.eye(ka, ka + 1, dtype=bool)
+                a[off] *= min(1.0, 4.0 / ka)
+            b0 = L.operand(rng, dtype, n, m + 2)
+            L.check_trxm(oracle, sim, (dtype, solve, side, uplo, trans, unit, m, n, ka + 1, m + 2, alpha), a, b0)
