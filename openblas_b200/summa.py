@@ -111,12 +111,6 @@ def panel_schedule(k, nb, P, Q):
     return steps
 
 
-def merge_panels(steps, nb, kb, P, Q):
-    """Coarsen the schedule to panels of up to kb columns when a single owner holds them
-    contiguously (P == 1 or Q == 1 along that axis); otherwise keep block-sized panels."""
-    return steps  # block-sized panels are the unit; kb == nb is chosen by the caller
-
-
 class Summa:
     """C_loc <- alpha * sum_k A_panel(k) * B_panel(k) + beta * C_loc on a P x Q grid.
 
