@@ -1,6 +1,8 @@
 /*
- * level3_aux.cu -- the two HBM-bound helper kernels behind SYMM/HEMM and the SYRK family
- * (runtime_level3.inl).  Both are plain coalesced passes over an n x n matrix: 32 x 8 thread
+ * level3_aux.cu -- the helper kernels behind the rest of level 3 (runtime_level3.inl): three HBM-bound
+ * passes (expand_symmetric, tri_merge, real_diagonal) and the 64 x 64 triangular block kernel of
+ * TRMM / TRSM (tri_block_kernel, described where it is defined).  The first two are plain coalesced
+ * passes over an n x n matrix: 32 x 8 thread
  * blocks walk columns (the contiguous direction of column-major storage) so every warp reads and
  * writes 128 / 256 / 512 contiguous bytes; the grid is sized to the matrix, capped at a multiple
  * of the SM count with a grid-stride loop.

@@ -1,17 +1,22 @@
 /*
- * runtime_level3.inl -- device side of SYMM/HEMM, SYRK/HERK, SYR2K/HER2K (included by runtime.cu
- * inside namespace b200).  These routines share the GEMM kernels in the reference too
+ * runtime_level3.inl -- device side of SYMM/HEMM, SYRK/HERK, SYR2K/HER2K, TRMM/TRSM (included by
+ * runtime.cu inside namespace b200).  These routines share the GEMM kernels in the reference too
  * (driver/level3/symm_k.c runs the GEMM loop nest over a symmetric packer; level3_syrk.c and
- * level3_syr2k.c run it over the triangle with syrk_kernel.c masking the diagonal blocks); here:
+ * level3_syr2k.c run it over the triangle with syrk_kernel.c masking the diagonal blocks; trmm_L.c /
+ * trsm_L.c block the triangular matrix around the same micro-kernel); here:
  *
  *   SYMM / HEMM   the referenced triangle is expanded ONCE into a full matrix in workspace
  *                 (O(ka^2) bytes of HBM traffic against O(ka^2 * n) flops) and the product is one
  *                 GEMM at the GEMM kernels' speed;
- *   SYRK family   C is cut into block columns of width NB.  The rectangle strictly inside the
- *                 triangle is a plain GEMM straight into C; the NB x NB diagonal block is computed
- *                 in full into a scratch tile and merged under the triangle mask (tri_merge), which
- *                 also applies beta and, for HERK/HER2K, zeroes the diagonal's imaginary part.
- *                 Wasted flops: NB / n of the total.
+ *   SYRK family   preferred: ONE GEMM launch per product whose kernel walks only the tiles of the
+ *                 triangle and masks the stores of the tiles the diagonal crosses (DeviceGemm::tri).
+ *                 Fallback when the eligible kernel cannot mask (tiny or unaligned problems): C is cut
+ *                 into block columns of width NB; the rectangle strictly inside the triangle is a
+ *                 plain GEMM straight into C, the NB x NB diagonal block is computed in full into a
+ *                 scratch tile and merged under the triangle mask (tri_merge), which also applies
+ *                 beta and, for HERK/HER2K, zeroes the diagonal's imaginary part;
+ *   TRMM / TRSM   recursive halving of op(A) around one large GEMM per level, 64 x 64 diagonal
+ *                 blocks in tri_block_kernel (see tri_recurse below).
  *
  * Host operands are staged whole (A, B, and the full m x n rectangle of C -- the part of C
  * outside the triangle travels up and comes back bit-identical; rows beyond m never move).
