@@ -325,6 +325,11 @@ int b200_init(int device);
 void *b200_host_alloc(size_t bytes);
 void  b200_host_free(void *p);
 
+/* Releases everything the library holds on the GPU and the host (pooled streams, events, device workspace,
+ * pinned staging, the host copy threads); also runs as the library's destructor.  Replaces gotoblas_quit
+ * (driver/others/memory.c:1566-1600).  The next call initialises again. */
+void b200_shutdown(void);
+
 /* Version string, e.g. "openblas_b200 0.1 (sm_100a)". */
 const char *b200_version(void);
 

@@ -18,6 +18,8 @@
  */
 #include "gemm_common.cuh"
 #include "async_copy.cuh"
+#include "sgemm_ws.cuh"
+#include <cstdlib>
 
 namespace b200 {
 namespace {
@@ -220,6 +222,8 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
   return cudaGetLastError();
 }
 
+typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true> CwsConfig;
+
 }  // namespace
 
 cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
@@ -231,6 +235,22 @@ cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   const int vec_b = (((uintptr_t)g.b & 15) == 0) && (g.ldb % 2 == 0);
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
   cudaError_t e;
+  /* Full grids go to the warp-specialised TMA kernel shared with SGEMM (sgemm_ws.cuh, CPLX: 128 x 64 complex
+   * tiles, 8 x 4 complex per thread): same wave-count rule as launch_sgemm_ffma.  B200_CGEMM_TILE=64|128 forces
+   * the 64 x 64 kernel / the TMA kernel. */
+  {
+    const char *ev = getenv("B200_CGEMM_TILE");
+    const int forced = ev ? atoi(ev) : 0;
+    const int64_t sms = sm_count();
+    int64_t t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64), tws = ((g.m + 127) / 128) * ((g.n + 63) / 64);
+    if (g.tri) { t64 = (t64 + 1) / 2; tws = (tws + 1) / 2; }
+    const double est64 = (double)((t64 + sms - 1) / sms), estws = 2.0 * 0.9 * (double)((tws + sms - 1) / sms);   /* per-SM work in 64 x 64 tiles */
+    if (sws::eligible(g) && (forced == 128 || (forced == 0 && estws <= est64))) {
+      e = sws::launch<CwsConfig, true>(g, stream);
+      if (e == cudaSuccess) { count_launch("cgemm_ffma2_ws_tma_128x64x16"); return e; }
+      if (e != cudaErrorNotSupported) return e;
+    }
+  }
   if (a_mn && b_mn) e = launch_variant<true, true>(g, stream, vec_a, vec_b, vec_c);
   else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream, vec_a, vec_b, vec_c);
   else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream, vec_a, vec_b, vec_c);

@@ -86,6 +86,10 @@ cudaError_t launch_zgemm_dmma(const DeviceGemm &g, cudaStream_t stream);
 cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream);
 cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream);
 cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t stream);
+/* gemm_batch: one launch over every tile of every problem (device arrays; first_tile has count + 1 entries) */
+int64_t generic_tile_count(int64_t m, int64_t n);
+cudaError_t launch_grouped(int dtype, const DeviceGemm *problems_dev, const int64_t *first_tile_dev, int count, int64_t tiles,
+                           cudaStream_t stream);
 cudaError_t launch_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
                            int64_t inc_out, cudaStream_t stream);
 

@@ -72,21 +72,17 @@ __device__ __forceinline__ double2 epi(double2 acc, double2 old, double ar, doub
   return r;
 }
 
+/* one TILE x TILE tile of C at (m0, n0); every thread of the CTA takes part */
 template <int DT>
-__global__ void __launch_bounds__(TPB)
-gemm_generic_kernel(DeviceGemm g) {
+__device__ __forceinline__ void generic_tile(const DeviceGemm &g, const int64_t m0, const int64_t n0,
+                                             typename Traits<DT>::Out (*As)[TILE + 1], typename Traits<DT>::Out (*Bs)[TILE + 1]) {
   using In = typename Traits<DT>::In;
   using Out = typename Traits<DT>::Out;    /* also the accumulator type */
   using Real = typename Traits<DT>::Real;
 
-  __shared__ Out As[KSTEP][TILE + 1];
-  __shared__ Out Bs[KSTEP][TILE + 1];
-
   const In *A = (const In *)g.a;
   const In *B = (const In *)g.b;
   Out *C = (Out *)g.c;
-  const int64_t m0 = (int64_t)blockIdx.x * TILE;
-  const int64_t n0 = (int64_t)blockIdx.y * TILE;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const bool ta = g.transa & 1, ca = g.transa & 2;
   const bool tb = g.transb & 1, cb = g.transb & 2;
@@ -156,6 +152,48 @@ gemm_generic_kernel(DeviceGemm g) {
   }
 }
 
+
+/* Tiles are numbered along m first; a 1-D grid-stride walk, so any m and n launch (a 2-D grid would cap
+ * n at 65535 tiles: m = 8, n = 3 000 000 is a legal call) */
+template <int DT>
+__global__ void __launch_bounds__(TPB)
+gemm_generic_kernel(DeviceGemm g) {
+  using Out = typename Traits<DT>::Out;
+  __shared__ Out As[KSTEP][TILE + 1];
+  __shared__ Out Bs[KSTEP][TILE + 1];
+  const int64_t tiles_m = (g.m + TILE - 1) / TILE, tiles = tiles_m * ((g.n + TILE - 1) / TILE);
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    generic_tile<DT>(g, (t % tiles_m) * TILE, (t / tiles_m) * TILE, As, Bs);
+    __syncthreads();
+  }
+}
+
+/* gemm_batch: ONE launch walks every tile of every matrix of the batch (interface/gemm_batch.c:322-366
+ * queues one job per matrix for the thread pool; here the job list lives in device memory).
+ * first_tile[i] = number of tiles of problems 0..i-1; a CTA finds its problem by bisection. */
+template <int DT>
+__global__ void __launch_bounds__(TPB)
+gemm_grouped_kernel(const DeviceGemm *__restrict__ problems, const int64_t *__restrict__ first_tile, int count) {
+  using Out = typename Traits<DT>::Out;
+  __shared__ Out As[KSTEP][TILE + 1];
+  __shared__ Out Bs[KSTEP][TILE + 1];
+  __shared__ __align__(16) unsigned char g_bytes[sizeof(DeviceGemm)];     /* raw bytes: DeviceGemm has a default member initialiser */
+  DeviceGemm &g = *reinterpret_cast<DeviceGemm *>(g_bytes);
+  const int64_t tiles = first_tile[count];
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first_tile[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    if (threadIdx.x == 0) g = problems[lo];
+    __syncthreads();
+    const int64_t local = t - first_tile[lo], tiles_m = (g.m + TILE - 1) / TILE;
+    generic_tile<DT>(g, (local % tiles_m) * TILE, (local / tiles_m) * TILE, As, Bs);
+    __syncthreads();
+  }
+}
+
 /* bf16 <-> fp32/fp64 conversion; rounding rule of kernel/x86_64/tobf16.c:46-96:
  * round-to-nearest-even, input denormals -> signed zero, NaN -> quiet NaN. */
 __device__ __forceinline__ uint16_t f32_to_bf16(float f) {
@@ -205,9 +243,10 @@ __global__ void convert_kernel(int dir, int64_t n, const void *in, int64_t inc_i
 
 }  // namespace
 
+static unsigned grid_for(int64_t tiles) { return (unsigned)(tiles < 0x7fffffffll ? (tiles > 0 ? tiles : 1) : 0x7fffffffll); }
+
 cudaError_t launch_generic(const DeviceGemm &g, cudaStream_t stream) {
-  dim3 grid((unsigned)((g.m + TILE - 1) / TILE), (unsigned)((g.n + TILE - 1) / TILE));
-  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
+  const unsigned grid = grid_for(((g.m + TILE - 1) / TILE) * ((g.n + TILE - 1) / TILE));
   switch (g.dtype) {
     case B200_S:  gemm_generic_kernel<B200_S><<<grid, TPB, 0, stream>>>(g); break;
     case B200_D:  gemm_generic_kernel<B200_D><<<grid, TPB, 0, stream>>>(g); break;
@@ -217,6 +256,24 @@ cudaError_t launch_generic(const DeviceGemm &g, cudaStream_t stream) {
     default: return cudaErrorInvalidValue;
   }
   count_launch("gemm_generic");
+  return cudaGetLastError();
+}
+
+int64_t generic_tile_count(int64_t m, int64_t n) { return ((m + TILE - 1) / TILE) * ((n + TILE - 1) / TILE); }
+
+cudaError_t launch_grouped(int dtype, const DeviceGemm *problems_dev, const int64_t *first_tile_dev, int count, int64_t tiles,
+                           cudaStream_t stream) {
+  if (count <= 0 || tiles <= 0) return cudaSuccess;
+  const unsigned grid = grid_for(tiles);
+  switch (dtype) {
+    case B200_S:  gemm_grouped_kernel<B200_S><<<grid, TPB, 0, stream>>>(problems_dev, first_tile_dev, count); break;
+    case B200_D:  gemm_grouped_kernel<B200_D><<<grid, TPB, 0, stream>>>(problems_dev, first_tile_dev, count); break;
+    case B200_C:  gemm_grouped_kernel<B200_C><<<grid, TPB, 0, stream>>>(problems_dev, first_tile_dev, count); break;
+    case B200_Z:  gemm_grouped_kernel<B200_Z><<<grid, TPB, 0, stream>>>(problems_dev, first_tile_dev, count); break;
+    case B200_SB: gemm_grouped_kernel<B200_SB><<<grid, TPB, 0, stream>>>(problems_dev, first_tile_dev, count); break;
+    default: return cudaErrorInvalidValue;
+  }
+  count_launch("gemm_grouped");
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@
 #include <thread>
 #include <condition_variable>
 #include <functional>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,7 +91,9 @@ struct Context {
   static const int kSlots = 3;
   char *in_slot[kSlots] = {nullptr, nullptr, nullptr};
   char *out_slot[kSlots] = {nullptr, nullptr, nullptr};
-  cudaEvent_t in_ev[kSlots], out_ev[kSlots];
+  size_t in_slot_bytes = 0, out_slot_bytes = 0;   /* grown on demand up to B200_SLOT_BYTES: a 1024^3 call pins 3 x 8 MB, not 6 x 32 MB */
+  cudaEvent_t in_ev[kSlots] = {nullptr, nullptr, nullptr}, out_ev[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t order_ev = nullptr;                 /* orders the compute stream after the caller's legacy-stream work */
   bool in_busy[kSlots] = {false, false, false};
   int in_next = 0, out_next = 0;
   struct PendingOut { bool active = false; char *host; size_t hpitch, width, cols; };
@@ -133,27 +136,66 @@ static int ensure_init() {
   return 0;
 }
 
-static int acquire(Context **out) {
+static thread_local bool t_foreign = false;   /* classify() met device memory this library cannot reach */
+
+/* A lease binds the calling thread to the library's device for the duration of one call (the reference
+ * has no such notion; a caller thread's current device may differ from the one the first call bound the
+ * library to) and returns the context to the pool afterwards -- scrubbed if the call failed half-way, so
+ * a pooled context never carries pending copy-outs into someone else's call. */
+struct ContextLease {
+  Context *c = nullptr;
+  int prev_device = -1;
+  bool failed = false;
+  ~ContextLease();
+};
+
+static int acquire(ContextLease *lease) {
   int err = ensure_init();
   if (err) return err;
+  const int dev = g_device.load(std::memory_order_acquire);
+  int cur = dev;
+  CK(cudaGetDevice(&cur));
+  if (cur != dev) { CK(cudaSetDevice(dev)); lease->prev_device = cur; }
+  t_foreign = false;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_free_ctx.empty()) { *out = g_free_ctx.back(); g_free_ctx.pop_back(); return 0; }
+    if (!g_free_ctx.empty()) { lease->c = g_free_ctx.back(); g_free_ctx.pop_back(); return 0; }
   }
-  CK(cudaSetDevice(g_device.load(std::memory_order_acquire)));
   Context *c = new Context();
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  *out = c;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return set_error(e, "cudaStreamCreateWithFlags"); }
+  lease->c = c;
   return 0;
+}
+static void scrub(Context *c) {
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->s_in) cudaStreamSynchronize(c->s_in);
+  if (c->s_out) cudaStreamSynchronize(c->s_out);
+  cudaGetLastError();
+  for (int k = 0; k < Context::kSlots; k++) { c->out_pending[k].active = false; c->in_busy[k] = false; }
 }
 static void release(Context *c) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_free_ctx.push_back(c);
 }
-struct ContextLease {
-  Context *c = nullptr;
-  ~ContextLease() { if (c) release(c); }
-};
+ContextLease::~ContextLease() {
+  if (c) { if (failed) scrub(c); release(c); }
+  if (prev_device >= 0) cudaSetDevice(prev_device);
+}
+
+/* The BLAS call is synchronous and works on "the operands as of now".  A device-resident operand may
+ * still be being produced by work the caller queued earlier; our streams are non-blocking, so nothing
+ * orders us after it implicitly.  An event recorded on the LEGACY default stream completes after
+ * everything queued so far on it and on every blocking stream; the compute stream waits for that
+ * event on the device.  (Round 1 called cudaDeviceSynchronize() here, which also stalled the host until
+ * every other caller's stream had drained.)  Work queued on the caller's own NON-blocking streams is
+ * the caller's to synchronise -- or use b200_gemm_async on that stream. */
+static int order_after_caller(Context *c) {
+  if (!c->order_ev) CK(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->order_ev, cudaStreamLegacy));
+  CK(cudaStreamWaitEvent(c->stream, c->order_ev, 0));
+  return 0;
+}
 
 static int reserve_device(Context *c, size_t bytes) {
   if (bytes <= c->dws_bytes) return 0;
@@ -223,7 +265,23 @@ static PtrKind classify(const void *p) {
   cudaPointerAttributes at;
   cudaError_t e = cudaPointerGetAttributes(&at, p);
   if (e != cudaSuccess) { cudaGetLastError(); return PTR_PAGEABLE; }
-  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+  if (at.type == cudaMemoryTypeDevice) {
+    const int dev = g_device.load(std::memory_order_acquire);
+    if (at.device != dev) {
+      /* memory of another GPU: usable in place only over peer access (NVLink) */
+      cudaError_t pe = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        snprintf(t_error, sizeof t_error, "operand %p lives on device %d, the library is bound to device %d and peer access is unavailable (%s)",
+                 p, at.device, dev, cudaGetErrorName(pe));
+        t_foreign = true;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    return PTR_DEVICE;
+  }
+  if (at.type == cudaMemoryTypeManaged) return PTR_DEVICE;
   if (at.type == cudaMemoryTypeHost) return PTR_PINNED;
   return PTR_PAGEABLE;
 }
@@ -262,16 +320,23 @@ static const size_t kSlotBytes = B200_SLOT_BYTES;
 
 class HostPool {
  public:
-  static HostPool &get() { static HostPool *p = new HostPool(); return *p; }   /* leaked on purpose: no join at exit */
+  static HostPool &get() {                     /* never destroyed; stop() joins the workers */
+    static std::once_flag once;
+    std::call_once(once, [] { instance() = new HostPool(); });
+    return *instance();
+  }
+  static HostPool *&instance() { static HostPool *p = nullptr; return p; }
   /* run fn(i) for i in [0, n) on the pool plus the calling thread */
   void parallel_for(int64_t n, const std::function<void(int64_t)> &fn) {
     if (n <= 0) return;
     if (n == 1 || workers_.empty()) { for (int64_t i = 0; i < n; i++) fn(i); return; }
     std::unique_lock<std::mutex> lk(mu_);
     while (busy_) done_cv_.wait(lk);           /* one job at a time; concurrent callers queue up */
-    busy_ = true; fn_ = &fn; n_ = n; next_ = 0; left_ = n; gen_++;
+    busy_ = true; fn_ = &fn; n_ = n; next_ = 0; left_ = n;
+    gen_.fetch_add(1, std::memory_order_release);
+    const bool wake = sleepers_ > 0;
     lk.unlock();
-    work_cv_.notify_all();
+    if (wake) work_cv_.notify_all();
     run_some();
     lk.lock();
     while (left_ > 0) done_cv_.wait(lk);
@@ -279,11 +344,30 @@ class HostPool {
     lk.unlock();
     done_cv_.notify_all();
   }
+  /* workers still spinning after a recent job pick the next one up in microseconds; sleeping ones take up
+   * to milliseconds to wake on a virtualised host */
+  bool hot() { std::lock_guard<std::mutex> lk(mu_); return !workers_.empty() && sleepers_ == 0 && gen_.load() > 0; }
+  /* wake sleeping workers without giving them work: they spin for the next millisecond, so the copies that
+   * follow (the next chunk of this call, the next call of a loop) find them hot */
+  void poke() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (workers_.empty() || busy_ || sleepers_ == 0) return;
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    work_cv_.notify_all();
+  }
+  void stop() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_.store(true); }
+    work_cv_.notify_all();
+    for (std::thread &t : workers_) if (t.joinable()) t.join();
+    workers_.clear();
+  }
  private:
   HostPool() {
     unsigned hc = std::thread::hardware_concurrency();
     int n = (int)(hc / 2); if (n > 7) n = 7; if (n < 1) n = 0;
-    for (int i = 0; i < n; i++) { workers_.emplace_back([this] { loop(); }); workers_.back().detach(); }
+    for (int i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
   }
   void run_some() {
     for (;;) {
@@ -296,14 +380,34 @@ class HostPool {
   void loop() {
     uint64_t seen = 0;
     for (;;) {
-      { std::unique_lock<std::mutex> lk(mu_); while (gen_ == seen) work_cv_.wait(lk); seen = gen_; }
+      /* spin for a millisecond after the last job (a benchmark loop or a solver issues the next call
+       * right away), then sleep */
+      const auto t0 = std::chrono::steady_clock::now();
+      bool got = false;
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(1000)) {
+        if (gen_.load(std::memory_order_acquire) != seen || stop_.load(std::memory_order_relaxed)) { got = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> lk(mu_);
+        sleepers_++;
+        while (gen_.load(std::memory_order_acquire) == seen && !stop_.load()) work_cv_.wait(lk);
+        sleepers_--;
+      }
+      if (stop_.load()) return;
+      seen = gen_.load(std::memory_order_acquire);
       run_some();
     }
   }
   std::mutex mu_; std::condition_variable work_cv_, done_cv_;
   std::vector<std::thread> workers_;
   const std::function<void(int64_t)> *fn_ = nullptr;
-  int64_t n_ = 0, next_ = 0, left_ = 0; uint64_t gen_ = 0; bool busy_ = false;
+  int64_t n_ = 0, next_ = 0, left_ = 0; bool busy_ = false;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<bool> stop_{false};
+  int sleepers_ = 0;
 };
 
 /* columns [0, cols) of `width` bytes each, pitches in bytes */
@@ -312,7 +416,12 @@ static void host_copy_cols(char *dst, size_t dpitch, const char *src, size_t spi
   /* waking sleeping pool threads costs up to milliseconds on a virtualised host (measured: a 1024^3
    * DGEMM call went from 2 ms to 16 ms when its 8 MB operands were split over the pool), so only
    * copies of at least 16 MB are shared out */
-  int64_t parts = total >= B200_POOL_BYTES ? (int64_t)(total / (B200_POOL_BYTES / 8)) : 1;
+  /* spinning workers (a call finished less than a millisecond ago) take shares of 512 KB; otherwise 2 MB shares
+   * from 16 MB up */
+  const bool hot = HostPool::get().hot();
+  if (!hot && total >= B200_POOL_BYTES / 16) HostPool::get().poke();
+  const size_t share_at = hot ? B200_POOL_BYTES / 16 : B200_POOL_BYTES, share = hot ? B200_POOL_BYTES / 32 : B200_POOL_BYTES / 8;
+  int64_t parts = total >= share_at ? (int64_t)(total / share) : 1;
   if (parts > 16) parts = 16;
   if ((size_t)parts > cols) parts = (int64_t)cols;
   if (parts < 1) parts = 1;
@@ -323,14 +432,32 @@ static void host_copy_cols(char *dst, size_t dpitch, const char *src, size_t spi
   });
 }
 
-static int ensure_slots(Context *ctx) {
-  if (ctx->in_slot[0]) return 0;
-  for (int i = 0; i < Context::kSlots; i++) {
-    CK(cudaHostAlloc((void **)&ctx->in_slot[i], kSlotBytes, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void **)&ctx->out_slot[i], kSlotBytes, cudaHostAllocDefault));
-    CK(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ctx->out_ev[i], cudaEventDisableTiming));
+static int drain_all_out(Context *ctx);
+
+/* in / out slot rings, grown to the size this transfer needs (at most B200_SLOT_BYTES each) */
+static int ensure_slots(Context *ctx, bool out, size_t transfer_bytes) {
+  size_t want = round_up(transfer_bytes < (size_t)1 ? 1 : transfer_bytes, (size_t)1 << 20);
+  if (want > kSlotBytes) want = kSlotBytes;
+#ifdef B200_HOSTSIM
+  want = kSlotBytes;
+#endif
+  size_t &have = out ? ctx->out_slot_bytes : ctx->in_slot_bytes;
+  if (have >= want) return 0;
+  char **slot = out ? ctx->out_slot : ctx->in_slot;
+  cudaEvent_t *ev = out ? ctx->out_ev : ctx->in_ev;
+  if (have) {                                    /* growing: nothing may still be in flight through the old slots */
+    if (ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->s_in) CK(cudaStreamSynchronize(ctx->s_in));
+    if (ctx->s_out) CK(cudaStreamSynchronize(ctx->s_out));
+    if (out) { int e = drain_all_out(ctx); if (e) return e; }
+    for (int i = 0; i < Context::kSlots; i++) { CK(cudaFreeHost(slot[i])); slot[i] = nullptr; if (!out) ctx->in_busy[i] = false; }
+    have = 0;
   }
+  for (int i = 0; i < Context::kSlots; i++) {
+    CK(cudaHostAlloc((void **)&slot[i], want, cudaHostAllocDefault));
+    if (!ev[i]) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  have = want;
   return 0;
 }
 
@@ -354,13 +481,14 @@ static int h2d_any(Context *ctx, cudaStream_t s, PtrKind kind, char *dev, size_t
     CK(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, width, cols, cudaMemcpyHostToDevice, s));
     return 0;
   }
-  int err = ensure_slots(ctx);
-  if (err) return err;
-  size_t cpc = kSlotBytes / width;                 /* columns per chunk */
-  if (cpc == 0) {                                   /* a single column larger than a slot: let the driver stage it */
+  if (kSlotBytes / width == 0) {                    /* a single column larger than a slot: let the driver stage it */
     CK(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, width, cols, cudaMemcpyHostToDevice, s));
     return 0;
   }
+  /* slots of a third of the transfer: the pool fills slot i + 1 while the DMA engine drains slot i */
+  int err = ensure_slots(ctx, false, width * cols / 3 > width ? width * cols / 3 : width);
+  if (err) return err;
+  const size_t cpc = ctx->in_slot_bytes / width;    /* columns per chunk */
   for (size_t c0 = 0; c0 < cols; c0 += cpc) {
     const size_t nc = cols - c0 < cpc ? cols - c0 : cpc;
     const int k = ctx->in_next; ctx->in_next = (k + 1) % Context::kSlots;
@@ -380,9 +508,9 @@ static int d2h_any(Context *ctx, cudaStream_t s, PtrKind kind, char *host, size_
     CK(cudaMemcpy2DAsync(host, hpitch, dev, dpitch, width, cols, cudaMemcpyDeviceToHost, s));
     return 0;
   }
-  int err = ensure_slots(ctx);
+  int err = ensure_slots(ctx, true, width * cols / 3 > width ? width * cols / 3 : width);
   if (err) return err;
-  const size_t cpc = kSlotBytes / width;
+  const size_t cpc = ctx->out_slot_bytes / width;
   for (size_t c0 = 0; c0 < cols; c0 += cpc) {
     const size_t nc = cols - c0 < cpc ? cols - c0 : cpc;
     const int k = ctx->out_next; ctx->out_next = (k + 1) % Context::kSlots;
@@ -514,10 +642,11 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
   B.kind = product ? classify(p->b) : PTR_DEVICE;
   C.kind = classify(p->c);
 
-  /* The BLAS call is synchronous and works on "the operands as of now".  A device-resident operand may
-   * still be being produced by work the caller queued on its own streams (our streams are
-   * non-blocking, so nothing orders us after it implicitly): wait for the device first. */
-  if ((product && (A.kind == PTR_DEVICE || B.kind == PTR_DEVICE)) || C.kind == PTR_DEVICE) CK(cudaDeviceSynchronize());
+  if (t_foreign) return (int)cudaErrorInvalidDevice;
+  if ((product && (A.kind == PTR_DEVICE || B.kind == PTR_DEVICE)) || C.kind == PTR_DEVICE) {
+    int e = order_after_caller(ctx);
+    if (e) return e;
+  }
 
   Operand *ops[3] = {&A, &B, &C};
   const void *user[3] = {p->a, p->b, p->c};
@@ -624,10 +753,12 @@ B200_HIDDEN int b200_run_problem(const b200_problem *p) {
     if (!product && g.beta_re == 1.0 && g.beta_im == 0.0) return 0;
   }
   ContextLease lease;
-  int err = acquire(&lease.c);
+  int err = acquire(&lease);
   if (err) return err;
   t_error[0] = 0;
-  return run_on_context(lease.c, p);
+  err = run_on_context(lease.c, p);
+  lease.failed = err != 0;
+  return err;
 }
 
 B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
@@ -638,10 +769,12 @@ B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
     if (!trxm && !product && p->beta[0] == 1.0 && p->beta[1] == 0.0) return 0;
   }
   ContextLease lease;
-  int err = acquire(&lease.c);
+  int err = acquire(&lease);
   if (err) return err;
   t_error[0] = 0;
-  return run_level3_on_context(lease.c, p);
+  err = run_level3_on_context(lease.c, p);
+  lease.failed = err != 0;
+  return err;
 }
 
 /* gemm_batch (interface/gemm_batch.c:322-366 hands one queue entry per matrix to the thread pool):
@@ -650,6 +783,38 @@ B200_HIDDEN int b200_run_level3(const b200_l3_problem *p) {
  * blocks come back in ONE copy -- one synchronisation per batch instead of one per matrix.  A batch
  * whose operands are all device memory is launched back to back and synchronised once.  Anything
  * else (mixed host / device operands, huge matrices) runs matrix by matrix. */
+/* A batch of SMALL matrices (every m, n <= 128, one precision) is ONE launch of the grouped kernel
+ * (gemm_generic.cu): the problem list and its tile prefix sums are built in pinned memory at `hdesc`,
+ * copied to `ddesc`, and a 1-D grid walks all tiles of all matrices.  1000 x 64^3 DGEMMs: 50 ms as 1000
+ * launches of the roofline kernel (one or four CTAs each), well under a millisecond grouped. */
+static bool batch_is_groupable(const b200_problem *p, int64_t count) {
+  static const bool enabled = !(getenv("B200_BATCH_GROUPED") && atoi(getenv("B200_BATCH_GROUPED")) == 0);
+  if (!enabled || count < 2 || g_forced_kernel.load(std::memory_order_relaxed) == B200_K_FAST) return false;
+  for (int64_t i = 0; i < count; i++)
+    if (p[i].dtype != p[0].dtype || p[i].m > 128 || p[i].n > 128) return false;
+  return true;
+}
+static size_t grouped_desc_bytes(size_t count) { return round_up(count * sizeof(DeviceGemm) + (count + 1) * sizeof(int64_t), 256); }
+/* fills the descriptor block at hdesc (the caller uploads it to ddesc, before the launch, on stream s) */
+static int64_t fill_batch_desc(const std::vector<DeviceGemm> &gs, char *hdesc) {
+  const size_t count = gs.size();
+  DeviceGemm *hp = (DeviceGemm *)hdesc;
+  int64_t *ht = (int64_t *)(hdesc + count * sizeof(DeviceGemm));
+  int64_t tiles = 0;
+  for (size_t i = 0; i < count; i++) {
+    const DeviceGemm &g = gs[i];
+    memcpy(&hp[i], &g, sizeof g);
+    ht[i] = tiles;
+    const bool product = g.k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
+    if (product || !(g.beta_re == 1.0 && g.beta_im == 0.0)) tiles += generic_tile_count(g.m, g.n);   /* C := 1 * C: no tiles, C keeps its bits */
+  }
+  ht[count] = tiles;
+  return tiles;
+}
+static cudaError_t launch_batch_grouped(int dtype, size_t count, int64_t tiles, const char *ddesc, cudaStream_t s) {
+  return launch_grouped(dtype, (const DeviceGemm *)ddesc, (const int64_t *)(ddesc + count * sizeof(DeviceGemm)), (int)count, tiles, s);
+}
+
 static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, bool *handled) {
   *handled = false;
   static const bool enabled = !(getenv("B200_BATCH_PACKED") && atoi(getenv("B200_BATCH_PACKED")) == 0);
@@ -659,8 +824,8 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
   size_t ab_bytes = 0, c_bytes = 0;
   bool any_beta = false;
 
-  /* every operand already on the device: no staging at all -- wait once for whatever the caller has in
-   * flight, launch every matrix on one stream, synchronise once */
+  /* every operand already on the device: no staging at all -- order after whatever the caller has in
+   * flight, launch on one stream (one grouped launch when the matrices are small), synchronise once */
   {
     bool all_device = true;
     for (int64_t i = 0; i < count && all_device; i++) {
@@ -669,15 +834,28 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
       const bool product = p[i].k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
       all_device = classify(p[i].c) == PTR_DEVICE && (!product || (classify(p[i].a) == PTR_DEVICE && classify(p[i].b) == PTR_DEVICE));
     }
+    if (t_foreign) return (int)cudaErrorInvalidDevice;
     if (all_device) {
-      CK(cudaDeviceSynchronize());
+      int oe = order_after_caller(ctx);
+      if (oe) return oe;
+      std::vector<DeviceGemm> gs((size_t)count);
       for (int64_t i = 0; i < count; i++) {
         const b200_problem &q = p[i];
-        DeviceGemm g;
+        DeviceGemm &g = gs[(size_t)i];
         g.dtype = q.dtype; g.transa = q.transa; g.transb = q.transb; g.m = q.m; g.n = q.n; g.k = q.k;
         g.a = q.a; g.b = q.b; g.c = q.c; g.lda = q.lda; g.ldb = q.ldb; g.ldc = q.ldc;
         read_scalars(&q, g);
-        CK(dispatch(g, ctx->stream));
+      }
+      if (batch_is_groupable(p, count)) {
+        const size_t db = grouped_desc_bytes((size_t)count);
+        int err = reserve_device(ctx, db);
+        if (err) return err;
+        if ((err = reserve_pinned(ctx, db))) return err;
+        const int64_t tiles = fill_batch_desc(gs, ctx->hws);
+        CK(cudaMemcpyAsync(ctx->dws, ctx->hws, db, cudaMemcpyHostToDevice, ctx->stream));
+        CK(launch_batch_grouped(gs[0].dtype, gs.size(), tiles, ctx->dws, ctx->stream));
+      } else {
+        for (const DeviceGemm &g : gs) CK(dispatch(g, ctx->stream));
       }
       CK(cudaStreamSynchronize(ctx->stream));
       *handled = true;
@@ -710,12 +888,16 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
       else c_bytes += round_up(x.bytes_dev(), 256);
     }
   }
+  /* packed block: [problem list (grouped launch only) | all A and B | all C]; the list rides in the same upload */
+  const bool grouped = batch_is_groupable(p, count);
+  const size_t desc_bytes = grouped ? grouped_desc_bytes((size_t)count) : 0;
+  ab_bytes += desc_bytes;
   const size_t total = ab_bytes + c_bytes;
   if (total > B200_BATCH_BYTES) return 0;
   int err = reserve_device(ctx, total);
   if (err) return err;
   if ((err = reserve_pinned(ctx, total))) return err;
-  size_t off_ab = 0, off_c = ab_bytes;
+  size_t off_ab = desc_bytes, off_c = ab_bytes;
   for (Item &it : items) {
     if (it.product) {
       it.A.dev = ctx->dws + off_ab; pack_to(ctx->hws + off_ab, it.A); off_ab += round_up(it.A.bytes_dev(), 256);
@@ -728,12 +910,20 @@ static int run_batch_packed(Context *ctx, const b200_problem *p, int64_t count, 
     off_c += round_up(it.C.bytes_dev(), 256);
   }
   cudaStream_t s = ctx->stream;
-  const size_t up = any_beta ? total : ab_bytes;
-  if (up) CK(cudaMemcpyAsync(ctx->dws, ctx->hws, up, cudaMemcpyHostToDevice, s));
+  std::vector<DeviceGemm> gs;
+  gs.reserve(items.size());
   for (Item &it : items) {
     DeviceGemm &g = it.g;
     g.a = it.A.dev; g.b = it.B.dev; g.c = it.C.dev; g.lda = it.A.ld_dev; g.ldb = it.B.ld_dev; g.ldc = it.C.ld_dev;
-    CK(dispatch(g, s));
+    gs.push_back(g);
+  }
+  const int64_t tiles = grouped ? fill_batch_desc(gs, ctx->hws) : 0;
+  const size_t up = any_beta ? total : ab_bytes;
+  if (up) CK(cudaMemcpyAsync(ctx->dws, ctx->hws, up, cudaMemcpyHostToDevice, s));
+  if (grouped) {
+    CK(launch_batch_grouped(gs[0].dtype, gs.size(), tiles, ctx->dws, s));
+  } else {
+    for (const DeviceGemm &g : gs) CK(dispatch(g, s));
   }
   if (c_bytes) CK(cudaMemcpyAsync(ctx->hws + ab_bytes, ctx->dws + ab_bytes, c_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -762,31 +952,30 @@ B200_HIDDEN int b200_run_batch(const b200_problem *p, int64_t count) {
     if (!any) return 0;
   }
   ContextLease lease;
-  int err = acquire(&lease.c);
+  int err = acquire(&lease);
   if (err) return err;
   t_error[0] = 0;
   bool handled = false;
-  if ((err = run_batch_packed(lease.c, p, count, &handled))) return err;
+  if ((err = run_batch_packed(lease.c, p, count, &handled))) { lease.failed = true; return err; }
   if (handled) return 0;
   for (int64_t i = 0; i < count; i++) {
     err = run_on_context(lease.c, &p[i]);
-    if (err) return err;
+    if (err) { lease.failed = true; return err; }
   }
   return 0;
 }
 
-B200_HIDDEN int b200_run_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
-                                 int64_t inc_out) {
+static int run_convert_on_context(Context *ctx, int dir, int64_t n, const void *in, int64_t inc_in, void *out, int64_t inc_out) {
   static const size_t in_sz[4] = {4, 8, 2, 2}, out_sz[4] = {2, 2, 4, 8};
-  ContextLease lease;
-  int err = acquire(&lease.c);
-  if (err) return err;
-  Context *ctx = lease.c;
+  if (n <= 0) return 0;
+  /* increment 0 (the reference's loops then touch element 0 only): every output takes in[0]; every input lands
+   * in out[0], the last one winning */
+  if (inc_out == 0 && n > 1) { in = (const char *)in + (n - 1) * inc_in * (int64_t)in_sz[dir]; n = 1; }
   cudaStream_t s = ctx->stream;
-  int64_t ainc_in = inc_in < 0 ? -inc_in : inc_in, ainc_out = inc_out < 0 ? -inc_out : inc_out;
-  if (ainc_in == 0) ainc_in = 1;
-  if (ainc_out == 0) ainc_out = 1;
+  const int64_t ainc_in = inc_in < 0 ? -inc_in : inc_in, ainc_out = inc_out < 0 ? -inc_out : inc_out;
   bool in_dev = classify(in) == PTR_DEVICE, out_dev = classify(out) == PTR_DEVICE;
+  if (t_foreign) return (int)cudaErrorInvalidDevice;
+  if (in_dev || out_dev) { int e = order_after_caller(ctx); if (e) return e; }
   /* spans in elements of the strided arrays; the interface already moved negative-increment
    * pointers to the lowest address and the kernel walks with the signed increment */
   size_t in_bytes = ((size_t)(n - 1) * ainc_in + 1) * in_sz[dir];
@@ -795,6 +984,7 @@ B200_HIDDEN int b200_run_convert(int dir, int64_t n, const void *in, int64_t inc
   char *out_lo = (char *)out + (inc_out < 0 ? (n - 1) * inc_out * (int64_t)out_sz[dir] : 0);
   size_t in_off = 0, out_off = round_up(in_bytes, 256);
   size_t need = (in_dev ? 0 : out_off) + (out_dev ? 0 : round_up(out_bytes, 256));
+  int err;
   if (need) { err = reserve_device(ctx, out_off + round_up(out_bytes, 256)); if (err) return err; }
   const char *d_in_lo = in_dev ? in_lo : ctx->dws + in_off;
   char *d_out_lo = out_dev ? out_lo : ctx->dws + out_off;
@@ -807,6 +997,16 @@ B200_HIDDEN int b200_run_convert(int dir, int64_t n, const void *in, int64_t inc
   if (!out_dev) CK(cudaMemcpyAsync(out_lo, d_out_lo, out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
+}
+
+B200_HIDDEN int b200_run_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
+                                 int64_t inc_out) {
+  ContextLease lease;
+  int err = acquire(&lease);
+  if (err) return err;
+  err = run_convert_on_context(lease.c, dir, n, in, inc_in, out, inc_out);
+  lease.failed = err != 0;
+  return err;
 }
 
 B200_HIDDEN void b200_fatal(const char *where, int err) {
@@ -855,6 +1055,51 @@ B200_EXPORT int b200_init(int device) {
   }
   return ensure_init();
 }
+
+/* The counterpart of gotoblas_quit (driver/others/memory.c:1566-1600, the reference's library destructor):
+ * frees every pooled context (streams, events, device workspace, pinned staging and slot rings) and joins the
+ * host copy pool.  Safe to call with no call in flight; the next call initialises again. */
+static void shutdown_impl(void) {
+  if (g_device.load(std::memory_order_acquire) < 0 || getpid() != g_init_pid) return;
+  if (HostPool::instance()) HostPool::instance()->stop();
+  std::vector<Context *> ctxs;
+  { std::lock_guard<std::mutex> lk(g_mu); ctxs.swap(g_free_ctx); }
+  int cur = -1;
+  const int dev = g_device.load(std::memory_order_acquire);
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) cudaSetDevice(dev); else cur = -1;
+  /* at process exit the CUDA runtime may be gone already: then its objects are gone with it */
+  bool cuda_alive = true;
+  if (!ctxs.empty() && ctxs[0]->stream) {
+    const cudaError_t q = cudaStreamQuery(ctxs[0]->stream);
+    cuda_alive = q == cudaSuccess || q == cudaErrorNotReady;
+    cudaGetLastError();
+  }
+  for (Context *c : ctxs) {
+    if (!cuda_alive) { delete c; continue; }
+    scrub(c);
+    if (c->dws) cudaFree(c->dws);
+    if (c->hws) cudaFreeHost(c->hws);
+    for (int i = 0; i < Context::kSlots; i++) {
+      if (c->in_slot[i]) cudaFreeHost(c->in_slot[i]);
+      if (c->out_slot[i]) cudaFreeHost(c->out_slot[i]);
+      if (c->in_ev[i]) cudaEventDestroy(c->in_ev[i]);
+      if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]);
+    }
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->order_ev) cudaEventDestroy(c->order_ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    delete c;
+  }
+  cudaGetLastError();
+  if (cur >= 0) cudaSetDevice(cur);
+}
+/* at unload / exit; the CUDA runtime may already be shutting down, in which case the frees fail harmlessly */
+B200_EXPORT void b200_shutdown(void) { shutdown_impl(); }
+/* (calls the internal function, not the exported symbol: another copy of the library in the process -- the
+ * host-simulation build of the tests -- must not be reached through the PLT) */
+__attribute__((destructor)) static void b200_library_destructor(void) { shutdown_impl(); }
 
 B200_EXPORT void *b200_host_alloc(size_t bytes) {
   void *p = nullptr;

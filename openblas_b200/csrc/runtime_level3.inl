@@ -209,7 +209,8 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   A.kind = product ? classify(p->a) : PTR_DEVICE;
   B.kind = use_b ? classify(p->b) : PTR_DEVICE;
   C.kind = classify(p->c);
-  if ((product && A.kind == PTR_DEVICE) || (use_b && B.kind == PTR_DEVICE) || C.kind == PTR_DEVICE) CK(cudaDeviceSynchronize());
+  if (t_foreign) return (int)cudaErrorInvalidDevice;
+  if ((product && A.kind == PTR_DEVICE) || (use_b && B.kind == PTR_DEVICE) || C.kind == PTR_DEVICE) { int oe = order_after_caller(ctx); if (oe) return oe; }
 
   Operand *ops[3] = {&A, &B, &C};
   const void *user[3] = {p->a, p->b, p->c};

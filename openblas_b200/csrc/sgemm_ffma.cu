@@ -19,6 +19,7 @@
  */
 #include "gemm_common.cuh"
 #include "async_copy.cuh"
+#include "sgemm_ws.cuh"
 #include <cstdlib>
 
 namespace b200 {
@@ -485,6 +486,11 @@ cudaError_t launch_ops(const DeviceGemm &g, cudaStream_t stream, int vec_a, int 
   return launch_variant<TILE, false, false, PACKED>(g, stream, vec_a, vec_b, vec_c);
 }
 
+/* 8 consumer warps (2 x 4, warp tile 128 x 32, 16 x 8 per thread, 224 registers via setmaxnreg) + a producer
+ * warpgroup (one feeder warp per operand, 56 registers), 5-stage ring of 24 KB stages, fragments of the next
+ * stage prefetched under the last FMA block of the current one. */
+typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true> WsConfig;
+
 }  // namespace
 
 cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
@@ -517,10 +523,21 @@ cudaError_t launch_sgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
   const int forced = tv ? atoi(tv) : 0;
   const int64_t sms = sm_count();
   int64_t t128 = ((g.m + 127) / 128) * ((g.n + 127) / 128), t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64);
-  if (g.tri) { t128 = (t128 + 1) / 2; t64 = (t64 + 1) / 2; }
+  int64_t t256 = ((g.m + 255) / 256) * ((g.n + 127) / 128);
+  if (g.tri) { t128 = (t128 + 1) / 2; t64 = (t64 + 1) / 2; t256 = (t256 + 1) / 2; }
   const double penalty = (a_mn && b_mn) ? 1.15 : (!a_mn && !b_mn) ? 1e9 : 1.3;
   const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = penalty * (double)((t64 + sms - 1) / sms);   /* per-SM work */
-  const bool small_tile = packed == 1 && (forced == 64 || (forced != 128 && est64 < est128));
+  /* The warp-specialised TMA kernel (sgemm_ws.cuh: 256 x 128 tiles, 16 x 8 per thread, one CTA per SM) runs
+   * at 61-62 TFLOP/s on full grids against 53-55 for the 128 x 128 kernel (profiles/r02_sgemm_lab_and_ffma_probe.txt),
+   * i.e. a 256 x 128 tile costs 8 x 0.87 units of 64 x 64 work; it takes the problem when that beats the
+   * other tilings' wave counts and TMA can address the operands.  B200_SGEMM_TILE=256 forces it. */
+  const double est256 = 8.0 * 0.87 * (double)((t256 + sms - 1) / sms);
+  if (packed == 1 && sws::eligible(g) && (forced == 256 || (forced == 0 && est256 <= est128 && est256 <= est64))) {
+    e = sws::launch<WsConfig>(g, stream);
+    if (e == cudaSuccess) { count_launch("sgemm_ffma2_ws_tma_256x128x16"); return e; }
+    if (e != cudaErrorNotSupported) return e;
+  }
+  const bool small_tile = packed == 1 && (forced == 64 || (forced != 128 && forced != 256 && est64 < est128));
   if (small_tile) {
     e = launch_ops<64, 1>(g, stream, vec_a, vec_b, vec_c);
     if (e == cudaSuccess) count_launch("sgemm_ffma2_64x64x16");

@@ -19,8 +19,9 @@
 #include <mutex>
 
 namespace {
-std::mutex g_mu;
-std::map<const char *, std::pair<size_t, int>> g_blocks;   /* base -> (bytes, 1 device / 2 pinned) */
+/* leaked on purpose: the library's destructor (b200_shutdown) frees blocks at exit, after static destructors ran */
+std::mutex &g_mu = *new std::mutex;
+std::map<const char *, std::pair<size_t, int>> &g_blocks = *new std::map<const char *, std::pair<size_t, int>>;   /* base -> (bytes, 1 device / 2 pinned) */
 size_t g_device_bytes = 0;
 std::atomic<size_t> g_copies{0};
 
@@ -87,6 +88,10 @@ cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t 
 
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }

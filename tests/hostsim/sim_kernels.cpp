@@ -48,7 +48,7 @@ cudaError_t sim_gemm(const DeviceGemm &g, const char *name) {
       for (int64_t i = 0; i < g.m; i++)
         if (tri_keep(g.tri, i, j)) memcpy((char *)g.c + ((size_t)i + (size_t)j * g.ldc) * es, &t[((size_t)i + (size_t)j * g.m) * es], es);
   }
-  count_launch(name);
+  if (name) count_launch(name);
   return cudaSuccess;
 }
 
@@ -111,6 +111,19 @@ template <class T> void tri_block(int solve, int nb, int64_t nrhs, int eff_lower
 }  // namespace
 
 cudaError_t launch_generic(const DeviceGemm &g, cudaStream_t) { return g.tri ? cudaErrorNotSupported : sim_gemm(g, "sim_generic"); }
+int64_t generic_tile_count(int64_t m, int64_t n) { return ((m + 31) / 32) * ((n + 31) / 32); }
+/* the grouped kernel: the problem list and tile prefix sums are read from "device" memory, as the real kernel does */
+cudaError_t launch_grouped(int dtype, const DeviceGemm *problems, const int64_t *first_tile, int count, int64_t tiles, cudaStream_t) {
+  if (first_tile[count] != tiles) return cudaErrorInvalidValue;
+  for (int i = 0; i < count; i++) {
+    if (problems[i].dtype != dtype) return cudaErrorInvalidValue;
+    if (first_tile[i + 1] == first_tile[i]) continue;            /* no tiles: C untouched */
+    if (first_tile[i + 1] - first_tile[i] != generic_tile_count(problems[i].m, problems[i].n)) return cudaErrorInvalidValue;
+    sim_gemm(problems[i], nullptr);
+  }
+  count_launch("sim_grouped");
+  return cudaSuccess;
+}
 cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t) {
   if (g.dtype != B200_D || (((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & 7)) return cudaErrorNotSupported;
   const bool bulk_ok = g.lda % 2 == 0 && g.ldb % 2 == 0 && ((((uintptr_t)g.a | (uintptr_t)g.b) & 15) == 0);

@@ -105,9 +105,10 @@ def test_every_staging_path_equals_the_oracle_bitwise(sim, oracle, dtype):
     assert es_out in (4, 8, 16)
 
 
-def test_gemm_batch_is_staged_in_one_upload_and_one_download(sim, oracle):
+@pytest.mark.parametrize("one_big", [False, True])
+def test_gemm_batch_is_staged_in_one_upload_and_one_download(sim, oracle, one_big):
     rng = np.random.default_rng(9)
-    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2), (0, 0, 30, 20, 16, 4), (1, 1, 7, 5, 3, 4)]
+    groups = [(0, 1, 12, 9, 20, 3), (1, 0, 40, 33, 8, 2), (0, 0, 130 if one_big else 30, 20, 16, 4), (1, 1, 7, 5, 3, 4)]
     alphas, betas = [0.7, 1.0, -0.4, 2.0], [1.3, 0.0, 1.0, 0.0]
     cb = {0: 111, 1: 112}
     probs = []
@@ -126,8 +127,11 @@ def test_gemm_batch_is_staged_in_one_upload_and_one_download(sim, oracle):
                           ints([g[3] for g in groups]), ints([g[4] for g in groups]), (C.c_double * 4)(*alphas), ptrs(0),
                           ints([probs[f][1] for f in first]), ptrs(2), ints([probs[f][3] for f in first]), (C.c_double * 4)(*betas),
                           ptrs(5), ints([probs[f][6] for f in first]), len(groups), ints([g[5] for g in groups]))
-    assert sim.hostsim_copy_count() - copies == 2, "a packed batch is one H2D and one D2H"
-    assert sim.b200_launch_count() - launches == len(probs)
+    assert sim.hostsim_copy_count() - copies == 2, "a packed batch is one H2D (problem list included) and one D2H"
+    if one_big:     # a matrix beyond 128 rows: every matrix gets the kernel the dispatcher picks for it
+        assert sim.b200_launch_count() - launches == len(probs)
+    else:
+        assert sim.b200_launch_count() - launches == 1, "small matrices of one precision: one grouped launch for the whole batch"
     i = 0
     for gi, (ta, tb, m, n, k, cnt) in enumerate(groups):
         for _ in range(cnt):
@@ -386,9 +390,12 @@ print("child signal", os.WTERMSIG(status) if os.WIFSIGNALED(status) else 0, "exi
     assert "cannot be used after fork()" in r.stdout, r.stdout
 
 
-def test_gemm_batch_on_device_operands_needs_no_copies(sim, oracle):
+@pytest.mark.parametrize("m", [48, 136])
+def test_gemm_batch_on_device_operands_moves_no_matrix(sim, oracle, m):
+    """Device-resident batch: small matrices -> the problem list goes up (one small copy) and ONE grouped
+    launch runs; beyond 128 rows -> no copy at all, one launch per matrix."""
     rng = np.random.default_rng(21)
-    m, n, k, cnt = 48, 40, 36, 5
+    n, k, cnt = 40, 36, 5
     hosts, devs = [], []
     for _ in range(cnt):
         a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, 0, 1, m, n, k, pad=(2, 2, 2))
@@ -404,7 +411,10 @@ def test_gemm_batch_on_device_operands_needs_no_copies(sim, oracle):
     copies, launches = sim.hostsim_copy_count(), sim.b200_launch_count()
     sim.cblas_dgemm_batch(102, ints([111]), ints([112]), ints([m]), ints([n]), ints([k]), (C.c_double * 1)(0.7), vp(0), ints([hosts[0][1]]),
                           vp(1), ints([hosts[0][3]]), (C.c_double * 1)(1.3), vp(2), ints([hosts[0][5]]), 1, ints([cnt]))
-    assert sim.hostsim_copy_count() == copies and sim.b200_launch_count() - launches == cnt
+    if m <= 128:
+        assert sim.hostsim_copy_count() - copies == 1 and sim.b200_launch_count() - launches == 1
+    else:
+        assert sim.hostsim_copy_count() == copies and sim.b200_launch_count() - launches == cnt
     for (a, lda, b, ldb, c0, ldc), d in zip(hosts, devs):
         want = c0.copy()
         oracle.gemm(cpu.D, 0, 1, m, n, k, 0.7, a, lda, b, ldb, 1.3, want, ldc)

@@ -1,0 +1,154 @@
+"""GPU parity tests of the round-2 kernels and runtime paths, through the C ABI, against the oracle:
+the warp-specialised TMA SGEMM / CGEMM (sgemm_ws.cuh), the grouped gemm_batch kernel, the 1-D grid of
+the generic kernel, library shutdown / re-initialisation."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+from helpers import alpha_beta, ntrans, problem
+from test_gemm_gpu import CB, check
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad4(dtype, ta, tb, m, n, k):
+    """paddings that make lda, ldb multiples of 4 elements (TMA: 16-byte pitches) but not of the tile"""
+    ra, rb = (k if ta & 1 else m), (n if tb & 1 else k)
+    return (4 + (-ra) % 4, 8 + (-rb) % 4, 3)
+
+
+@pytest.mark.parametrize("dtype", [cpu.S, cpu.CX])
+def test_ws_tma_kernels_all_ops_ragged(ob, oracle, dtype, monkeypatch):
+    """sgemm_ws.cuh forced onto interior, ragged, k-tail and tiny shapes of every op combination (conj
+    included for CGEMM), beta != 0 and beta == 0 over a NaN C; device operands so that the kernel sees
+    exactly these leading dimensions."""
+    import torch
+    monkeypatch.setenv("B200_SGEMM_TILE" if dtype == cpu.S else "B200_CGEMM_TILE", "256" if dtype == cpu.S else "128")
+    rng = np.random.default_rng(4242 + dtype)
+    alphas, betas = alpha_beta(dtype)
+    for (m, n, k) in [(256, 128, 64), (300, 260, 200), (1000, 77, 513), (64, 64, 16), (513, 130, 17), (36, 20, 5)]:
+        for ta in range(ntrans(dtype)):
+            for tb in range(ntrans(dtype)):
+                a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=_pad4(dtype, ta, tb, m, n, k))
+                for alpha, beta in ((alphas[2], betas[2]), (alphas[1], 0.0)):
+                    start = c0.copy()
+                    if beta == 0.0:
+                        start[:, :m] = np.nan                     # beta == 0 never reads C
+                    da, db, dc = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(start.copy()).cuda()
+                    ob.cblas.gemm_any(dtype, ta, tb, m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc)
+                    kern = ob.cblas.last_kernel()
+                    assert "ws_tma" in kern, kern
+                    check(oracle, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, dc.cpu().numpy(), kern)
+
+
+@pytest.mark.parametrize("dtype", [cpu.S, cpu.CX])
+def test_ws_tma_kernels_are_the_default_on_full_grids(ob, oracle, dtype):
+    """2048 x 2048 x 96: enough 256 x 128 tiles for the dispatcher to pick the TMA kernel on its own; checked
+    against the oracle (k kept small: the CPU oracle is scalar code)."""
+    import torch
+    rng = np.random.default_rng(99 + dtype)
+    m = n = 2048
+    k = 96
+    for ta, tb in ((0, 0), (1, 0), (0, 1), (1, 1)) + (((3, 2),) if dtype == cpu.CX else ()):
+        a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(0, 0, 0))
+        alpha, beta = alpha_beta(dtype)[0][2], alpha_beta(dtype)[1][2]
+        da, db, dc = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c0.copy()).cuda()
+        ob.cblas.gemm_any(dtype, ta, tb, m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc)
+        kern = ob.cblas.last_kernel()
+        assert "ws_tma" in kern, kern
+        check(oracle, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, dc.cpu().numpy(), kern)
+
+
+def test_ssyrk_and_cherk_through_the_ws_kernel(ob, oracle, monkeypatch):
+    """The triangle mask (DeviceGemm::tri) of the TMA kernel: SSYRK / CSYRK / CHERK with the kernel forced,
+    the other triangle of C keeps its bits (checked by check_case)."""
+    import level3_helpers as L
+    monkeypatch.setenv("B200_SGEMM_TILE", "256")
+    monkeypatch.setenv("B200_CGEMM_TILE", "128")
+    monkeypatch.setenv("B200_RANKK_TRI", "1")
+    call = L.bind(ob.lib())
+    rng = np.random.default_rng(7)
+    for dtype, herm in ((cpu.S, 0), (cpu.CX, 0), (cpu.CX, 1)):
+        cplx = dtype == cpu.CX
+        for uplo in (0, 1):
+            for trans in (0, 1):
+                n, k = 300, 132
+                rows, cols = (k, n) if trans else (n, k)
+                a, c0 = L.operand(rng, dtype, cols, rows + 4), L.operand(rng, dtype, n, n + 3)
+                alpha, beta = ((0.7, 1.3) if herm or not cplx else (0.7 - 0.9j, 1.3 - 1.1j))
+                case = (1, dtype, herm, 0, uplo, trans, 0, n, k, rows + 4, rows + 4, n + 3, alpha, beta)
+                got, want, gauge, K, touched = L.run_case(call, oracle, case, a, a, c0)
+                L.check_case(case, got, want, gauge, K, touched, c0)
+                assert "ws_tma" in ob.cblas.last_kernel() or "diag" in ob.cblas.last_kernel(), ob.cblas.last_kernel()
+
+
+def test_generic_kernel_takes_skinny_problems_beyond_65535_column_tiles(ob):
+    """m < 16 forces the generic kernel; n / 32 > 65535 overflowed its 2-D grid in round 1 (ADVICE):
+    cblas_dgemm(m = 8, n = 2.2M, k = 2) must compute, not abort."""
+    import torch
+    m, n, k = 8, 2_200_000, 2
+    a = torch.rand((k, m), dtype=torch.float64, device="cuda") - 0.5          # column-major m x k
+    b = torch.rand((n, k), dtype=torch.float64, device="cuda") - 0.5          # column-major k x n
+    c = torch.full((n, m), float("nan"), dtype=torch.float64, device="cuda")
+    ob.cblas.gemm_any(cpu.D, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m)
+    assert ob.cblas.last_kernel() == "gemm_generic"
+    want = b @ a                                                              # (n x k) (k x m) = C^T as stored
+    assert torch.allclose(c, want, rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_grouped_batch_kernel(ob, oracle, where):
+    """200 small DGEMMs of mixed shapes in ONE launch (gemm_grouped), host operands (one packed upload) and
+    device operands; C := 1 * C members keep their bits; every matrix checked against the oracle."""
+    import torch
+    rng = np.random.default_rng(31)
+    shapes = [(0, 0, 64, 64, 64, 120), (1, 0, 33, 17, 40, 50), (0, 1, 128, 5, 3, 20), (1, 1, 9, 128, 70, 10)]
+    alphas, betas = [0.7, 1.0, 0.0, 2.0], [1.3, 0.0, 1.0, -0.5]
+    probs, keep = [], []
+    for gi, (ta, tb, m, n, k, cnt) in enumerate(shapes):
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, ta, tb, m, n, k, pad=(1, 1, 1))
+            start = c0.copy()
+            if betas[gi] == 0.0:
+                start[:, :m] = np.nan
+            if where == "device":
+                bufs = [torch.from_numpy(x).cuda() for x in (a, b, start)]
+                keep.append(bufs)
+                ptrs = [t.data_ptr() for t in bufs]
+            else:
+                ptrs = [a.ctypes.data, b.ctypes.data, start.ctypes.data]
+            probs.append((a, lda, b, ldb, c0, start, ldc, ptrs))
+    I = lambda vals: (C.c_int * len(vals))(*vals)
+    first = [sum(s[5] for s in shapes[:i]) for i in range(len(shapes))]
+    arr = lambda j: (C.c_void_p * len(probs))(*[p[7][j] for p in probs])
+    adr = lambda x: C.cast(x, C.c_void_p)
+    before = ob.cblas.launch_count()
+    ob.lib().cblas_dgemm_batch(ob.cblas.ColMajor, adr(I([CB[s[0]] for s in shapes])), adr(I([CB[s[1]] for s in shapes])),
+                               adr(I([s[2] for s in shapes])), adr(I([s[3] for s in shapes])), adr(I([s[4] for s in shapes])),
+                               adr((C.c_double * 4)(*alphas)), adr(arr(0)), adr(I([probs[f][1] for f in first])), adr(arr(1)),
+                               adr(I([probs[f][3] for f in first])), adr((C.c_double * 4)(*betas)), adr(arr(2)),
+                               adr(I([probs[f][6] for f in first])), len(shapes), adr(I([s[5] for s in shapes])))
+    assert ob.cblas.launch_count() - before == 1 and ob.cblas.last_kernel() == "gemm_grouped"
+    i = 0
+    for gi, (ta, tb, m, n, k, cnt) in enumerate(shapes):
+        for _ in range(cnt):
+            a, lda, b, ldb, c0, start, ldc, _p = probs[i]
+            got = keep[i][2].cpu().numpy() if where == "device" else start
+            i += 1
+            if alphas[gi] == 0.0 and betas[gi] == 1.0:
+                assert np.array_equal(got.view(np.uint8), c0.view(np.uint8)), "C := 1 * C must not touch C"
+            else:
+                check(oracle, cpu.D, ta, tb, m, n, k, alphas[gi], a, lda, b, ldb, betas[gi], c0, ldc, got, "grouped-" + where)
+
+
+def test_shutdown_releases_and_the_next_call_initialises_again(ob, oracle):
+    rng = np.random.default_rng(3)
+    m, n, k = 150, 140, 130
+    a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.D, 0, 0, m, n, k)
+    for _ in range(2):
+        got = c0.copy()
+        ob.cblas.dgemm(ob.cblas.ColMajor, CB[0], CB[0], m, n, k, 0.7, a, lda, b, ldb, 1.3, got, ldc)
+        check(oracle, cpu.D, 0, 0, m, n, k, 0.7, a, lda, b, ldb, 1.3, c0, ldc, got, "around-shutdown")
+        ob.lib().b200_shutdown()
