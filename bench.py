@@ -38,20 +38,50 @@ PEAK_FALLBACK = {"d": 36.8, "z": 36.8, "s": 71.1, "c": 71.1, "sb": 1590.0}
 NCU_TRAFFIC_BYTES = {("d", 16384, 16384, 16384): 54.017287e9 + 2.149455e9}
 
 
-def measured_peak(dtype):
+_INRUN_PEAKS = None
+
+
+def inrun_peaks(device=0):
+    """FP64 / FP32 dense peaks measured in THIS lease: tools/peaks (built by __graft_entry__.build) runs the
+    DMMA / FFMA / FFMA2 issue-rate probes and cuBLAS D/SGEMM (pedantic: no TF32) at 8192^3 on the same GPU,
+    before the benchmark touches it.  None when the tool is missing or fails (the committed round-1
+    measurement is used then, and the line says so)."""
+    global _INRUN_PEAKS
+    if _INRUN_PEAKS is not None:
+        return _INRUN_PEAKS or None
+    _INRUN_PEAKS = {}
+    exe = os.path.join(ROOT, "tools", "peaks")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, "quick", str(device)], capture_output=True, text=True, timeout=120)
+            if r.returncode == 0:
+                _INRUN_PEAKS = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            _INRUN_PEAKS = {}
+    return _INRUN_PEAKS or None
+
+
+def measured_peak(dtype, device=0):
+    """(peak TFLOP/s, where it comes from).  bf16: MEASURED_PEAKS.json (driver-written, burst).  FP64 / FP32:
+    MEASURED_PEAKS.json has no entry and B200_PROFILING.md states no fallback, so the denominator is the
+    issue rate of the pipe's own instruction measured in this run (DMMA.8x8x4 / FFMA), else the same probe's
+    committed round-1 result."""
     if dtype == "sb":
         try:
             p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             return float(p["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst)"
         except Exception:
             return PEAK_FALLBACK["sb"], "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+    key = "dmma_tflops" if dtype in ("d", "z") else "ffma_tflops"
+    what = "DMMA.8x8x4" if dtype in ("d", "z") else "FFMA"
+    p = inrun_peaks(device)
+    if p:
+        return max(v for k, v in p.items() if k.startswith(key)), f"{what} issue rate measured in this run by tools/peaks (MEASURED_PEAKS.json has no FP64/FP32 entry)"
     try:
         p = json.load(open(os.path.join(ROOT, "profiles", "r01_peaks_microbench.json")))
-        if dtype in ("d", "z"):
-            return max(p[k] for k in p if k.startswith("dmma_tflops")), "tools/peaks.cu DMMA issue-rate microbenchmark on this pool (MEASURED_PEAKS.json has no FP64 entry)"
-        return max(p[k] for k in p if k.startswith("ffma_tflops")), "tools/peaks.cu FFMA issue-rate microbenchmark on this pool (MEASURED_PEAKS.json has no FP32 entry)"
+        return max(v for k, v in p.items() if k.startswith(key)), f"{what} issue rate, tools/peaks result committed in round 1 (profiles/r01_peaks_microbench.json); the in-run probe was unavailable"
     except Exception:
-        return PEAK_FALLBACK[dtype], "tools/peaks.cu value recorded in bench.py"
+        return PEAK_FALLBACK[dtype], "tools/peaks value recorded in bench.py"
 
 
 class ClockSampler:
@@ -94,11 +124,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def workload_config(dtype, m, n, k, parallelism):
-    """The `config` object both arms print (same workload naming for the driver's ratio)."""
+def grid_of(world):
+    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4), 16: (4, 4)}.get(world, (1, world))
+
+
+def workload_config(dtype, m, n, k, world, nb):
+    """The `config` object BOTH arms print, key for key (the driver compares them): it names the workload,
+    not the arm.  What ran it is in `arm`."""
+    P, Q = grid_of(world)
     return {"workload": f"{dtype}gemm NN column-major {m}x{n}x{k} alpha=1 beta=0 (BASELINE configs[1] at N=1; configs[3] shape at N=8)",
-            "parallelism": parallelism, "l2_policy": "inputs larger than L2 (A,B >= 2 GiB each vs 126 MB L2)",
-            "inputs": "uniform(-0.5,0.5), fixed seed, resident in HBM"}
+            "parallelism": "one GEMM" if world == 1 else f"one GEMM, C distributed 2-D block-cyclically over a {P}x{Q} grid (nb={nb}) on the GPU arm",
+            "l2_policy": "inputs larger than L2 (A,B >= 2 GiB each vs 126 MB L2)",
+            "inputs": "uniform(-0.5,0.5), fixed seed"}
 
 
 def weak_shape(world):
@@ -108,6 +145,10 @@ def weak_shape(world):
 
 # ---------------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's own CPU GEMM on the box's host cores, all threads, on the SAME workload as the GPU arm
+    whenever (steps + warmup) calls of it fit in --ref-budget seconds (DGEMM 16384^3 is about 6 s per call
+    on 16 Sapphire Rapids cores); otherwise every dimension is halved until they do, and the line says so
+    (`same_workload` false, `reference_sample` in config)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -115,49 +156,66 @@ def run_reference(args):
     from oracle import cpu
     kind = "reference" if cpu.have_reference() else "port"
     dtype = args.dtype
-    n = args.ref_n
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(0)
     npdt = cpu.NP_IN[DT[dtype]]
+    wm, wn, wk = (args.m, args.n, args.k) if args.m else weak_shape(args.gpus)
 
-    def operand():
-        x = rng.random((n, n), dtype=np.float32) - 0.5
+    def operand(rows, cols):
+        x = rng.random((cols, rows), dtype=np.float32) - 0.5
         if dtype == "sb":
             return cpu.Oracle().tobf16(x)
         if dtype in ("c", "z"):
-            return (x + 1j * (rng.random((n, n), dtype=np.float32) - 0.5)).astype(npdt)
+            return (x + 1j * (rng.random((cols, rows), dtype=np.float32) - 0.5)).astype(npdt)
         return x.astype(npdt)
-    a, b = operand(), operand()
-    c = np.zeros((n, n), dtype=cpu.NP_OUT[DT[dtype]])
     if kind == "reference":
         ref = cpu.Reference()
         ref.set_threads(cores)
-        call = lambda: ref.gemm(DT[dtype], 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n)
+        gemm = lambda m, n, k, a, b, c: ref.gemm(DT[dtype], 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m)
         desc = f"oracle/_ref/{ref.target} ({ref.config()}), OPENBLAS_NUM_THREADS={cores}"
     else:
         orc = cpu.Oracle()
         cores = 1
-        call = lambda: orc.gemm(DT[dtype], 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n)
+        gemm = lambda m, n, k, a, b, c: orc.gemm(DT[dtype], 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m)
         desc = "oracle/gemm_oracle.c (scalar port, 1 thread)"
+    # calibration call (untimed for the result): rate of a small GEMM -> how much of the workload fits the budget
+    cn = 2048 if kind == "reference" else 256
+    ca, cb_, cc = operand(cn, cn), operand(cn, cn), np.zeros((cn, cn), dtype=cpu.NP_OUT[DT[dtype]])
+    gemm(cn, cn, cn, ca, cb_, cc)
+    t0 = time.perf_counter(); gemm(cn, cn, cn, ca, cb_, cc); rate = 2.0 * cn ** 3 / (time.perf_counter() - t0)
+    del ca, cb_, cc
+    m, n, k = wm, wn, wk
+    if args.ref_n:
+        m = n = k = args.ref_n
+    else:
+        calls = args.steps + args.warmup
+        while 2.0 * m * n * k / rate * calls > args.ref_budget and min(m, n, k) > 256:
+            m, n, k = max(256, m // 2), max(256, n // 2), max(256, k // 2)
+    same = (m, n, k) == (wm, wn, wk)
+    a, b = operand(m, k), operand(k, n)
+    c = np.zeros((n, m), dtype=cpu.NP_OUT[DT[dtype]])
+    call = lambda: gemm(m, n, k, a, b, c)
     for _ in range(args.warmup):
         call()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         call()
     dt = time.perf_counter() - t0
-    flops = 2.0 * n * n * n * args.steps      # BASELINE metric is 2mnk/t for every precision
+    flops = 2.0 * m * n * k * args.steps      # BASELINE metric is 2mnk/t for every precision
     val = flops / dt / 1e12
-    sample = f"{dtype.upper()}GEMM {n}^3 NN column-major alpha=1 beta=0 on host cores ({desc}); bounded sample of the {weak_shape(args.gpus)} workload"
-    wm, wn, wk = weak_shape(args.gpus)
-    cfg = workload_config(dtype, wm, wn, wk, "host CPU cores (reference arm)")
-    cfg["reference_sample"] = f"each step = one {dtype}gemm {n}x{n}x{n} NN alpha=1 beta=0 on the host cores (bounded sample of the workload above)"
+    sample = (f"{dtype.upper()}GEMM {m}x{n}x{k} NN column-major alpha=1 beta=0 on host cores ({desc}); "
+              + ("the full workload of the GPU arm" if same else f"bounded sample of the {wm}x{wn}x{wk} workload (rates, so comparable; {args.steps + args.warmup} full-size calls would exceed {args.ref_budget:.0f} s)"))
+    cfg = workload_config(dtype, wm, wn, wk, args.gpus, args.nb)
+    if not same:
+        cfg["reference_sample"] = f"each step = one {dtype}gemm {m}x{n}x{k} NN alpha=1 beta=0 on the host cores (bounded sample of the workload above)"
     print(json.dumps({
         "impl": "reference", "metric": f"{dtype.upper()}GEMM TFLOP/s (2mnk/t)", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"d": "f64", "s": "f32", "z": "c128", "c": "c64", "sb": "bf16->f32"}[dtype],
         "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "same_workload": same,
+        "arm": f"host CPU cores: {desc}",
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -211,6 +269,8 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; openblas_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if world == 1 and not args.no_peaks:
+        inrun_peaks(local_rank)          # FP64 / FP32 denominators, measured on the idle GPU before the benchmark
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -281,7 +341,7 @@ def run_gpu(args):
     # the event pair around it
     kern_ms = sorted(s.elapsed_time(e) for s, e in kern_ev)
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
-    peak, peak_src = measured_peak(dtype)
+    peak, peak_src = measured_peak(dtype, local_rank)
     real_flops_launch = FLOP_FACTOR[dtype] * (m * n * k if world == 1 else 0)
     # N > 1 end to end: every rank's shards start in pinned HOST memory; a step = H2D of the local A and B
     # pieces, the SUMMA sweep, D2H of the local C piece (all ranks take part, so it runs before the
@@ -320,13 +380,15 @@ def run_gpu(args):
         elif world > 1:
             e2e = e2e_multi
         cpu_b = cpu_baseline(dtype) if (world == 1 and not args.no_cpu) else None
+        parity = sampled_parity(torch, dtype, 0, 0, m, n, k, a, m, b, k, c, m) if world == 1 else None
+        extra = run_extras(ob, torch, dev, stream, args) if (world == 1 and not args.no_extras) else None
         achieved = (real_flops_launch / (kern_ms_avg * 1e-3) / 1e12) if world == 1 else (FLOP_FACTOR[dtype] * m * n * k / world / (total_ms / args.steps * 1e-3) / 1e12)
         out = {
             "metric": f"{dtype.upper()}GEMM TFLOP/s (2mnk/t)", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"d": "f64", "s": "f32", "z": "c128", "c": "c64", "sb": "bf16->f32"}[dtype], "data": "synthetic",
-            "config": workload_config(dtype, m, n, k, parallelism),
+            "config": workload_config(dtype, m, n, k, world, args.nb), "arm": parallelism,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get((dtype, m, n, k)) if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
                          "algorithmic_bytes": (2 if dtype == "sb" else {"s": 4, "d": 8, "c": 8, "z": 16}[dtype]) * (m * k + k * n) + {"s": 4, "d": 8, "c": 8, "z": 16, "sb": 4}[dtype] * m * n,
@@ -335,6 +397,12 @@ def run_gpu(args):
                          "note": "achieved = real flops of one launch (2mnk, 8mnk complex) / CUDA-event duration of that launch; per GPU at N>1"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity:
+            out["parity"] = parity
+        if world == 1:
+            out["peaks_in_run"] = inrun_peaks(local_rank)
+        if extra:
+            out["extra"] = extra
         if cpu_b:
             out["cpu_baseline"] = cpu_b
         if e2e:
@@ -344,6 +412,166 @@ def run_gpu(args):
         dist.destroy_process_group()
     if out:
         print(json.dumps(out))
+
+
+def sampled_parity(torch, dtype, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, samples=64, alpha=1.0, seed=7):
+    """`samples` entries of C = alpha * op(A) op(B) (beta = 0) recomputed on the host in long double from the
+    operands as they lie in HBM, outside every timed region.  Returns the worst ratio
+    |C - C_ref| / (k * eps * sum|a||b|): the north-star acceptance bound is ratio <= c with c = 2.
+    Column-major operands held as 2-D torch tensors (cols, ld)."""
+    import numpy as np
+    g = torch.Generator(); g.manual_seed(seed)
+    ii = torch.randint(0, m, (samples,), generator=g).tolist()
+    jj = torch.randint(0, n, (samples,), generator=g).tolist()
+    eps = 2.0 ** -52 if dtype in ("d", "z") else 2.0 ** -23
+    ld_t = np.clongdouble if dtype in ("c", "z") else np.longdouble
+
+    def host(t):
+        t = t.cpu()
+        if t.dtype == torch.bfloat16:
+            t = t.float()
+        return t.numpy().astype(ld_t)
+    worst = 0.0
+    for i, j in zip(ii, jj):
+        if ta & 1:
+            ar = host(a[i, :k])                 # op(A)(i, :) = column i of the stored k x m matrix
+        else:
+            ar = host(a[:k, i])                 # row i of the stored m x k matrix
+        if tb & 1:
+            bc = host(b[:k, j])
+        else:
+            bc = host(b[j, :k])
+        if ta & 2:
+            ar = np.conj(ar)
+        if tb & 2:
+            bc = np.conj(bc)
+        ref = alpha * np.dot(ar, bc)
+        gauge = float(abs(alpha) * np.dot(np.abs(ar), np.abs(bc)))
+        got = c[j, i].item()
+        worst = max(worst, float(abs(ld_t(got) - ref)) / (k * eps * gauge))
+    return {"worst_ratio": worst, "samples": samples, "bound": "|C - C_ref| <= 2 * k * eps * (|A||B|) per entry, C_ref in long double on the host",
+            "ok": worst <= 2.0}
+
+
+def device_time_ms(torch, fn, reps, stream):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_extras(ob, torch, dev, stream, args):
+    """The other north-star targets, measured in the same driver run as the headline (device-resident operands,
+    CUDA events on the launching stream, every result spot-checked against long-double dot products):
+    SBGEMM 8192^3 on the default kernel (burst and >= 2 s sustained), SGEMM 16384^3, ZGEMM / CGEMM 8192^3 (NN and
+    the other op combinations), the tall-skinny shapes of BASELINE config 5, DGEMM/SGEMM mid sizes of config 2."""
+    T = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128, "sb": torch.bfloat16}
+    ES = {"s": 4, "d": 8, "c": 8, "z": 16, "sb": 2}
+    gen = torch.Generator(device=dev); gen.manual_seed(4321)
+    hbm = None
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    def rand(cols, rows, dtype):
+        t = T[dtype]
+        if t.is_complex:                 # in place: the tall-skinny operands are 64 GiB each
+            return torch.view_as_complex(torch.rand((cols, rows, 2), generator=gen, device=dev, dtype=torch.float64 if dtype == "z" else torch.float32).sub_(0.5))
+        if dtype == "sb":
+            return torch.rand((cols, rows), generator=gen, device=dev, dtype=torch.float32).sub_(0.5).to(t)
+        return torch.rand((cols, rows), generator=gen, device=dev, dtype=t).sub_(0.5)
+
+    def one(dtype, ops, m, n, k, reps, check=True):
+        """every op combination in `ops` on an m x n x k problem; returns {op: TFLOP/s (real flops)}, kernel, parity"""
+        code = DT[dtype]
+        res, worst, kern = {}, 0.0, None
+        odt = torch.float32 if dtype == "sb" else T[dtype]
+        c = torch.empty((n, m), dtype=odt, device=dev)
+        for ta, tb in ops:
+            ra, ca = (k, m) if ta & 1 else (m, k)
+            rb, cb = (n, k) if tb & 1 else (k, n)
+            a, b = rand(ca, ra, dtype), rand(cb, rb, dtype)
+            f = lambda: ob.cblas.gemm_device(code, ta, tb, m, n, k, 1.0, a, ra, b, rb, 0.0, c, m, stream.cuda_stream)
+            for _ in range(3):
+                f()
+            torch.cuda.synchronize(dev)
+            ms = device_time_ms(torch, f, reps, stream)
+            res["NTRC"[ta] + "NTRC"[tb]] = FLOP_FACTOR[dtype] * m * n * k / (ms * 1e-3) / 1e12
+            kern = ob.cblas.last_kernel()
+            if check:
+                worst = max(worst, sampled_parity(torch, dtype, ta, tb, m, n, k, a, ra, b, rb, c, m, samples=16)["worst_ratio"])
+            del a, b
+        del c
+        return res, kern, worst
+
+    out = {}
+    NT4 = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    # (a) SBGEMM 8192^3, default kernel: burst = 20 back-to-back launches after warm-up; sustained = back to back for >= 2 s
+    m = n = k = 8192
+    a, b = rand(k, m, "sb"), rand(n, k, "sb")
+    c = torch.empty((n, m), dtype=torch.float32, device=dev)
+    f = lambda: ob.cblas.gemm_device(DT["sb"], 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m, stream.cuda_stream)
+    for _ in range(5):
+        f()
+    torch.cuda.synchronize(dev)
+    burst_ms = min(device_time_ms(torch, f, 20, stream) for _ in range(3))
+    reps = int(2.2 / (burst_ms * 1e-3)) + 1
+    sust_ms = device_time_ms(torch, f, reps, stream)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    pb, ps = float(peaks.get("bf16_tflops", PEAK_FALLBACK["sb"])), float(peaks.get("bf16_tflops_sustained", 0) or 0)
+    tf = lambda ms_: 2.0 * m * n * k / (ms_ * 1e-3) / 1e12
+    out["sbgemm_8192"] = {"kernel": ob.cblas.last_kernel(), "burst_tflops": tf(burst_ms), "burst_launches": 20, "sustained_tflops": tf(sust_ms),
+                          "sustained_launches": reps, "sustained_seconds": sust_ms * reps * 1e-3, "peak_burst": pb, "peak_sustained": ps or None,
+                          "frac_of_burst_peak": tf(burst_ms) / pb, "sustained_frac_of_sustained_peak": (tf(sust_ms) / ps) if ps else None,
+                          "sustained_frac_of_burst_peak": tf(sust_ms) / pb,
+                          "parity_worst_ratio": sampled_parity(torch, "sb", 0, 0, m, n, k, a, m, b, k, c, m, samples=16)["worst_ratio"]}
+    del a, b, c
+    r, kern, w = one("sb", [(1, 0), (0, 1), (1, 1)], 8192, 8192, 8192, 20)
+    out["sbgemm_8192"]["other_ops_tflops"] = r
+    out["sbgemm_8192"]["parity_worst_ratio"] = max(out["sbgemm_8192"]["parity_worst_ratio"], w)
+
+    # (b) FP32 / complex at the sizes the targets are quoted on
+    for key, dtype, size, ops, reps in (("sgemm_16384", "s", 16384, NT4, 3), ("zgemm_8192", "z", 8192, NT4 + [(3, 0), (3, 3)], 3),
+                                        ("cgemm_8192", "c", 8192, NT4 + [(3, 0), (3, 3)], 3)):
+        peak, src = measured_peak(dtype, dev.index or 0)
+        r, kern, w = one(dtype, ops, size, size, size, reps)
+        out[key] = {"tflops_real_flops": r, "tflops_2mnk": {o: v * 2.0 / FLOP_FACTOR[dtype] for o, v in r.items()}, "kernel": kern, "peak": peak,
+                    "frac": r["NN"] / peak, "worst_op": min(r, key=r.get), "worst_op_frac": min(r.values()) / peak, "parity_worst_ratio": w}
+    out["peak_source_fp32"] = measured_peak("s", dev.index or 0)[1]
+
+    # (c) BASELINE config 5, tall-skinny: flop bound and HBM bound side by side (algorithmic bytes = A + B + C once)
+    ts = {}
+    for dtype in ("z", "c"):
+        peak, _ = measured_peak(dtype, dev.index or 0)
+        for (mm, nn, kk) in ((65536, 256, 65536), (65536, 65536, 256)):
+            r, kern, w = one(dtype, [(0, 0), (3, 0)] if nn == 256 else [(0, 0)], mm, nn, kk, 3)
+            bytes_alg = ES[dtype] * (mm * kk + kk * nn + mm * nn)
+            flops = FLOP_FACTOR[dtype] * mm * nn * kk
+            t_flop, t_hbm = flops / (peak * 1e12), (bytes_alg / (hbm * 1e9)) if hbm else None
+            ts[f"{dtype}gemm_{mm}x{nn}x{kk}"] = {"tflops_real_flops": r, "tflops_2mnk": {o: v * 2.0 / FLOP_FACTOR[dtype] for o, v in r.items()}, "kernel": kern,
+                                                 "frac_of_flop_peak": r["NN"] / peak, "algorithmic_bytes": bytes_alg,
+                                                 "flop_bound_ms": t_flop * 1e3, "hbm_bound_ms": t_hbm * 1e3 if t_hbm else None,
+                                                 "measured_ms": flops / (r["NN"] * 1e12) * 1e3, "parity_worst_ratio": w}
+            torch.cuda.empty_cache()
+    out["tall_skinny"] = ts
+
+    # (d) BASELINE config 2 sweep, NN (the 16384^3 DGEMM point is the headline itself)
+    sw = {}
+    for dtype in ("d", "s"):
+        peak, _ = measured_peak(dtype, dev.index or 0)
+        for size in (1024, 2048, 4096, 8192):
+            r, kern, w = one(dtype, [(0, 0)], size, size, size, 20 if size <= 4096 else 5, check=size <= 4096)
+            sw[f"{dtype}gemm_{size}"] = {"tflops": r["NN"], "frac": r["NN"] / peak, "kernel": kern}
+    out["square_sweep_nn"] = sw
+    return out
 
 
 def run_e2e(ob, torch, code, dtype, m, n, k, tdt, odt, args):
@@ -476,9 +704,12 @@ def main():
     ap.add_argument("--dtype", default="d", choices=list(DT))
     ap.add_argument("--m", type=int, default=0); ap.add_argument("--n", type=int, default=0); ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--nb", type=int, default=2048, help="SUMMA distribution block / panel width")
-    ap.add_argument("--ref-n", type=int, default=8192, help="size of the bounded CPU sample of the reference arm")
+    ap.add_argument("--ref-n", type=int, default=0, help="reference arm: force an n^3 sample (default: the GPU arm's workload, halved only if it cannot fit --ref-budget)")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="reference arm: seconds the (steps + warmup) calls may take")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true"); ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra north-star measurements (SBGEMM, SGEMM, Z/C, tall-skinny, mid sizes)")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the in-run FP64/FP32 peak probe (tools/peaks quick)")
     ap.add_argument("--sweep", action="store_true"); ap.add_argument("--sizes", default="1024,2048,4096,8192,16384")
     ap.add_argument("--sweep-level3", action="store_true", help="developer view: SYMM/SYRK/SYR2K/HEMM/HERK on device operands")
     ap.add_argument("--sweep-dtypes", default="d,s,z,c,sb")

@@ -1067,15 +1067,7 @@ static void shutdown_impl(void) {
   int cur = -1;
   const int dev = g_device.load(std::memory_order_acquire);
   if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) cudaSetDevice(dev); else cur = -1;
-  /* at process exit the CUDA runtime may be gone already: then its objects are gone with it */
-  bool cuda_alive = true;
-  if (!ctxs.empty() && ctxs[0]->stream) {
-    const cudaError_t q = cudaStreamQuery(ctxs[0]->stream);
-    cuda_alive = q == cudaSuccess || q == cudaErrorNotReady;
-    cudaGetLastError();
-  }
   for (Context *c : ctxs) {
-    if (!cuda_alive) { delete c; continue; }
     scrub(c);
     if (c->dws) cudaFree(c->dws);
     if (c->hws) cudaFreeHost(c->hws);
@@ -1095,11 +1087,15 @@ static void shutdown_impl(void) {
   cudaGetLastError();
   if (cur >= 0) cudaSetDevice(cur);
 }
-/* at unload / exit; the CUDA runtime may already be shutting down, in which case the frees fail harmlessly */
 B200_EXPORT void b200_shutdown(void) { shutdown_impl(); }
-/* (calls the internal function, not the exported symbol: another copy of the library in the process -- the
- * host-simulation build of the tests -- must not be reached through the PLT) */
-__attribute__((destructor)) static void b200_library_destructor(void) { shutdown_impl(); }
+/* At unload / process exit only the host copy pool is joined.  No CUDA call is made from a library destructor:
+ * at exit the CUDA runtime's own teardown may already have run (in any order relative to ours), and touching a
+ * dead runtime crashes the process after main() has returned; the operating system reclaims the rest.  A program
+ * that dlclose()s the library mid-run calls b200_shutdown() first. */
+__attribute__((destructor)) static void b200_library_destructor(void) {
+  if (g_device.load(std::memory_order_acquire) < 0 || getpid() != g_init_pid) return;
+  if (HostPool::instance()) HostPool::instance()->stop();
+}
 
 B200_EXPORT void *b200_host_alloc(size_t bytes) {
   void *p = nullptr;

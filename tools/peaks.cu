@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <algorithm>
 
@@ -98,12 +99,19 @@ static double time_ms(F launch, int reps = 5) {
   return *std::min_element(t.begin(), t.end());
 }
 
-int main() {
-  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+/* peaks [quick] [device]: "quick" = issue rates at 8 and 16 warps/SM + cuBLAS D/S at 8192 only (a few seconds:
+ * bench.py runs it inside the benchmark lease so that the FP64 / FP32 roofline denominators are measured on the
+ * same box, same clocks, as the numbers they divide) */
+int main(int argc, char **argv) {
+  bool quick = false; int device = 0;
+  for (int i = 1; i < argc; i++) { if (!strcmp(argv[i], "quick")) quick = true; else device = atoi(argv[i]); }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
   int sms = p.multiProcessorCount;
   void *buf; CK(cudaMalloc(&buf, (size_t)sms * 8 * 1024 * 8));
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d", p.name, sms, p.clockRate);
   for (int warps : {4, 8, 16}) {
+    if (quick && warps == 4) continue;
     int threads = warps * 32, blocks = sms * 2;
     double tot_threads = (double)blocks * threads;
     double ms;
@@ -120,6 +128,7 @@ int main() {
 
   cublasHandle_t h; cublasCreate(&h);
   for (int n : {4096, 8192, 16384}) {
+    if (quick && n != 8192) continue;
     size_t bytes = (size_t)n * n * 8;
     double *a, *b, *c;
     if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess || cudaMalloc(&c, bytes) != cudaSuccess) break;
@@ -144,7 +153,7 @@ int main() {
     ms = time_ms([&] { cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &fone, (float *)a, n, (float *)b, n, &fzero, (float *)c, n); });
     printf(", \"cublas_sgemm_pedantic_tflops_%d\": %.2f", n, 2.0 * n * n * n / (ms * 1e-3) / 1e12);
     cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-    if (n == 8192) {
+    if (n == 8192 && !quick) {
       /* bf16 values: fill with small numbers to avoid NaN patterns */
       std::vector<__nv_bfloat16> hb((size_t)n * 64);
       for (auto &x : hb) x = __float2bfloat16((float)rand() / RAND_MAX - 0.5f);
