@@ -339,6 +339,7 @@ def run_gpu(args):
 
     # dominant kernel = the local GEMM; at N = 1 a step IS one launch, so the per-launch duration is
     # the event pair around it
+    main_kernel = ob.cblas.last_kernel()
     kern_ms = sorted(s.elapsed_time(e) for s, e in kern_ev)
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
     peak, peak_src = measured_peak(dtype, local_rank)
@@ -393,7 +394,7 @@ def run_gpu(args):
                          "traffic": NCU_TRAFFIC_BYTES.get((dtype, m, n, k)) if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
                          "algorithmic_bytes": (2 if dtype == "sb" else {"s": 4, "d": 8, "c": 8, "z": 16}[dtype]) * (m * k + k * n) + {"s": 4, "d": 8, "c": 8, "z": 16, "sb": 4}[dtype] * m * n,
                          "peak_source": peak_src,
-                         "kernel": ob.cblas.last_kernel(), "kernel_ms_avg": kern_ms_avg if world == 1 else None,
+                         "kernel": main_kernel, "kernel_ms_avg": kern_ms_avg if world == 1 else None,
                          "note": "achieved = real flops of one launch (2mnk, 8mnk complex) / CUDA-event duration of that launch; per GPU at N>1"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

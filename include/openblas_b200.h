@@ -246,6 +246,41 @@ void ctrsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasin
 void ztrsm_(char *SIDE, char *UPLO, char *TRANSA, char *DIAG, blasint *M, blasint *N, double *alpha, double *a, blasint *ldA,
             double *b, blasint *ldB);
 
+/* ---- ?GEMMT: the Uplo triangle of the M x M matrix C := alpha op(A) op(B) + beta C; the other
+ *      triangle of C is never read or written (cblas.h:311-318; common_interface.h:506-513;
+ *      interface/gemmt.c:67 Fortran, :200 CBLAS).  One triangle-masked launch of the GEMM kernels.  A and B are
+ *      never written (the reference conjugates one operand in place for ConjTrans / ConjNoTrans, gemmt.c:466-476). */
+void cblas_sgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                  blasint M, blasint K, float alpha, const float *A, blasint lda, const float *B, blasint ldb, float beta,
+                  float *C, blasint ldc);
+void cblas_dgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                  blasint M, blasint K, double alpha, const double *A, blasint lda, const double *B, blasint ldb, double beta,
+                  double *C, blasint ldc);
+void cblas_cgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                  blasint M, blasint K, const void *alpha, const void *A, blasint lda, const void *B, blasint ldb,
+                  const void *beta, void *C, blasint ldc);
+void cblas_zgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                  blasint M, blasint K, const void *alpha, const void *A, blasint lda, const void *B, blasint ldb,
+                  const void *beta, void *C, blasint ldc);
+void sgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, float *alpha, float *a, blasint *ldA, float *b,
+             blasint *ldB, float *beta, float *c, blasint *ldC);
+void dgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, double *alpha, double *a, blasint *ldA, double *b,
+             blasint *ldB, double *beta, double *c, blasint *ldC);
+void cgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, float *alpha, float *a, blasint *ldA, float *b,
+             blasint *ldB, float *beta, float *c, blasint *ldC);
+void zgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, double *alpha, double *a, blasint *ldA, double *b,
+             blasint *ldB, double *beta, double *c, blasint *ldC);
+
+/* ---- SBGEMV / SBDOT: bf16 operands, fp32 accumulation and result (cblas.h:441-442;
+ *      common_interface.h:62,258; interface/sbgemv.c, interface/bf16dot.c, kernel/x86_64/sbgemv_n.c, sbgemv_t.c,
+ *      sbdot.c).  HBM-bound CUDA kernels (csrc/bf16_level12.cu), deterministic (no atomics). */
+float cblas_sbdot(blasint n, const bfloat16 *x, blasint incx, const bfloat16 *y, blasint incy);
+void  cblas_sbgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, blasint m, blasint n, float alpha, const bfloat16 *a,
+                   blasint lda, const bfloat16 *x, blasint incx, float beta, float *y, blasint incy);
+float sbdot_(blasint *N, bfloat16 *x, blasint *INCX, bfloat16 *y, blasint *INCY);
+void  sbgemv_(char *TRANS, blasint *M, blasint *N, float *ALPHA, bfloat16 *a, blasint *LDA, bfloat16 *x, blasint *INCX,
+              float *BETA, float *y, blasint *INCY);
+
 /* ---- bf16 conversion helpers callers of sbgemm need (cblas.h:433-440;
  *      interface/tobf16.c, interface/bf16to.c; rounding rule kernel/x86_64/tobf16.c:46-96) */
 void cblas_sbstobf16(blasint n, const float *in, blasint incin, bfloat16 *out, blasint incout);

@@ -244,7 +244,10 @@ cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t stream) {
     const int64_t sms = sm_count();
     int64_t t64 = ((g.m + 63) / 64) * ((g.n + 63) / 64), tws = ((g.m + 127) / 128) * ((g.n + 63) / 64);
     if (g.tri) { t64 = (t64 + 1) / 2; tws = (tws + 1) / 2; }
-    const double est64 = (double)((t64 + sms - 1) / sms), estws = 2.0 * 0.9 * (double)((tws + sms - 1) / sms);   /* per-SM work in 64 x 64 tiles */
+    /* per-SM time in units of one 64 x 64 tile: the 64 x 64 kernel keeps two CTAs per SM, so its tiles go out in waves
+     * of 2 * sms that take two units each (2048^3: 1024 tiles = 4 waves of 296 -> 8 units, measured 46 TFLOP/s against
+     * 55 on full waves); a 128 x 64 tile of the TMA kernel is two units at 0.9 of the cost */
+    const double est64 = 2.0 * (double)((t64 + 2 * sms - 1) / (2 * sms)), estws = 2.0 * 0.9 * (double)((tws + sms - 1) / sms);
     if (sws::eligible(g) && (forced == 128 || (forced == 0 && estws <= est64))) {
       e = sws::launch<CwsConfig, true>(g, stream);
       if (e == cudaSuccess) { count_launch("cgemm_ffma2_ws_tma_128x64x16"); return e; }

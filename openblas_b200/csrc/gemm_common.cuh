@@ -93,6 +93,14 @@ cudaError_t launch_grouped(int dtype, const DeviceGemm *problems_dev, const int6
 cudaError_t launch_convert(int dir, int64_t n, const void *in, int64_t inc_in, void *out,
                            int64_t inc_out, cudaStream_t stream);
 
+/* bf16_level12.cu: SBGEMV / SBDOT on device pointers (x, y at their logical first element) */
+size_t sbgemv_workspace_bytes(int trans, int64_t m, int64_t n);
+cudaError_t launch_sbgemv(int trans, int64_t m, int64_t n, float alpha, const void *a, int64_t lda, const void *x, int64_t incx,
+                          float beta, void *y, int64_t incy, void *workspace, cudaStream_t stream);
+size_t sbdot_workspace_bytes();
+cudaError_t launch_sbdot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, void *workspace, float *result,
+                         cudaStream_t stream);
+
 /* level3_aux.cu: helpers of the symmetric level-3 family */
 cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out,
                                     int64_t ldo, cudaStream_t stream);

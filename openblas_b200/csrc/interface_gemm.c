@@ -299,3 +299,61 @@ B200_EXPORT void sbf16tos_(blasint *n, bfloat16 *in, blasint *incin, float *out,
                            blasint *incout) { convert(2, *n, in, *incin, 2, out, *incout, 4); }
 B200_EXPORT void dbf16tod_(blasint *n, bfloat16 *in, blasint *incin, double *out,
                            blasint *incout) { convert(3, *n, in, *incin, 2, out, *incout, 8); }
+
+/* ------------------------------------------------------------------- SBGEMV / SBDOT
+ * interface/sbgemv.c: flag decoding :76-79 (N, T, R = N, C = T) / :121-136 (row-major flips trans and swaps m, n);
+ * checks :81-86 / :138-143 in this order, xerbla_("SBGEMV ", &info, 8); m == 0 or n == 0 returns (:164); alpha == 0
+ * only scales y (:171-174); negative increments start from the far end (:179-180).
+ * interface/bf16dot.c: n <= 0 returns 0 (:14, :34). */
+static void sbgemv_entry(int cblas, int trans, int64_t m, int64_t n, float alpha, const bfloat16 *a, int64_t lda,
+                         const bfloat16 *x, int64_t incx, float beta, float *y, int64_t incy) {
+  blasint info = cblas ? -1 : 0;
+  char nm[9] = "SBGEMV ";
+  if (incy == 0) info = 11;
+  if (incx == 0) info = 8;
+  if (lda < (m > 1 ? m : 1)) info = 6;
+  if (n < 0) info = 3;
+  if (m < 0) info = 2;
+  if (trans < 0) info = 1;
+  if (cblas ? info >= 0 : info != 0) { xerbla_(nm, &info, 8); return; }
+  if (m == 0 || n == 0) return;
+  const int64_t lenx = trans ? m : n, leny = trans ? n : m;
+  if (incx < 0) x -= (lenx - 1) * incx;
+  if (incy < 0) y -= (leny - 1) * incy;
+  int err = b200_run_sbgemv(trans, m, n, alpha, a, lda, x, incx, beta, y, incy);
+  if (err) b200_fatal("SBGEMV", err);
+}
+
+B200_EXPORT void sbgemv_(char *TRANS, blasint *M, blasint *N, float *ALPHA, bfloat16 *a, blasint *LDA, bfloat16 *x,
+                         blasint *INCX, float *BETA, float *y, blasint *INCY) {
+  char t = *TRANS;
+  if (t >= 'a' && t <= 'z') t = (char)(t - 'a' + 'A');
+  const int trans = (t == 'N' || t == 'R') ? 0 : (t == 'T' || t == 'C') ? 1 : -1;
+  sbgemv_entry(0, trans, *M, *N, *ALPHA, a, *LDA, x, *INCX, *BETA, y, *INCY);
+}
+
+B200_EXPORT void cblas_sbgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE TransA, blasint m, blasint n, float alpha,
+                              const bfloat16 *a, blasint lda, const bfloat16 *x, blasint incx, float beta, float *y,
+                              blasint incy) {
+  int trans = -1;
+  const int nt = TransA == CblasNoTrans || TransA == CblasConjNoTrans, tr = TransA == CblasTrans || TransA == CblasConjTrans;
+  if (order == CblasColMajor) {
+    trans = nt ? 0 : tr ? 1 : -1;
+  } else {                      /* the reference treats every other order value as row-major (sbgemv.c:127) */
+    trans = nt ? 1 : tr ? 0 : -1;
+    blasint t = n; n = m; m = t;
+  }
+  sbgemv_entry(1, trans, m, n, alpha, a, lda, x, incx, beta, y, incy);
+}
+
+static float sbdot_entry(int64_t n, const bfloat16 *x, int64_t incx, const bfloat16 *y, int64_t incy) {
+  if (n <= 0) return 0.f;
+  if (incx < 0) x -= (n - 1) * incx;
+  if (incy < 0) y -= (n - 1) * incy;
+  float r = 0.f;
+  int err = b200_run_sbdot(n, x, incx, y, incy, &r);
+  if (err) b200_fatal("SBDOT", err);
+  return r;
+}
+B200_EXPORT float sbdot_(blasint *N, bfloat16 *x, blasint *INCX, bfloat16 *y, blasint *INCY) { return sbdot_entry(*N, x, *INCX, y, *INCY); }
+B200_EXPORT float cblas_sbdot(blasint n, const bfloat16 *x, blasint incx, const bfloat16 *y, blasint incy) { return sbdot_entry(n, x, incx, y, incy); }

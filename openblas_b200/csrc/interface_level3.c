@@ -136,6 +136,60 @@ static void rankk_entry(const char *name, int routine, int dtype, int cblas, int
   run(&p, name);
 }
 
+/* --------------------------------------------------------------------- GEMMT ---- */
+/* interface/gemmt.c: the uplo triangle of the m x m matrix C := alpha op(A) op(B) + beta C.  Flag decoding :124-161
+ * (Fortran) / :232-262 (CBLAS); row-major = the column-major problem with A and B swapped and uplo flipped (:305-345);
+ * checks :163-186 column-major, :365-389 row-major -- the row-major branch reports positions 10 / 8 for the leading
+ * dimensions it calls lda / ldb (the caller's LDB / LDA; the 10 test comes last) and 3 / 2 for the trans flags;
+ * xerbla_ gets sizeof("?GEMMT ") = 8; quick return m == 0 (:464).  The reference then walks the triangle column by
+ * column with GEMV (and conjugates its "b" operand IN PLACE for transb = R / C, :466-476, never undoing it -- not
+ * reproduced: inputs are const here); here it is ONE triangle-masked launch of the GEMM kernel. */
+static void gemmt_entry(const char *name, int dtype, int cblas, int order, int uplo, int transa, int transb, int64_t m,
+                        int64_t k, const double alpha[2], const void *a, int64_t lda, const void *b, int64_t ldb,
+                        const double beta[2], void *c, int64_t ldc) {
+  blasint info = cblas ? -1 : 0;
+  char nm[9];
+  memcpy(nm, name, 8);
+  nm[8] = 0;
+  if (cblas && order == CblasRowMajor) {
+    const void *t = a; a = b; b = t;
+    int64_t tl = lda; lda = ldb; ldb = tl;
+    int tt = transa; transa = transb; transb = tt;
+    uplo = flip(uplo);
+    const int64_t ncola = (transa >= 0 && (transa & 1)) ? k : m, ncolb = (transb >= 0 && (transb & 1)) ? m : k;
+    if (ldc < max1(m)) info = 13;
+    if (ldb < max1(ncolb)) info = 8;
+    if (lda < max1(ncola)) info = 10;
+    if (k < 0) info = 5;
+    if (m < 0) info = 4;
+    if (transb < 0) info = 2;
+    if (transa < 0) info = 3;
+    if (uplo < 0) info = 1;
+  } else if (cblas && order != CblasColMajor) {
+    info = 0;
+  } else {
+    const int64_t nrowa = (transa >= 0 && (transa & 1)) ? k : m, nrowb = (transb >= 0 && (transb & 1)) ? m : k;
+    if (ldc < max1(m)) info = 13;
+    if (ldb < max1(nrowb)) info = 10;
+    if (lda < max1(nrowa)) info = 8;
+    if (k < 0) info = 5;
+    if (m < 0) info = 4;
+    if (transb < 0) info = 3;
+    if (transa < 0) info = 2;
+    if (uplo < 0) info = 1;
+  }
+  if (cblas ? info >= 0 : info != 0) { xerbla_(nm, &info, 8); return; }
+  if (m == 0) return;
+
+  b200_l3_problem p;
+  memset(&p, 0, sizeof p);
+  p.routine = B200_GEMMT; p.dtype = dtype; p.uplo = uplo; p.trans = transa; p.transb = transb;
+  p.n = m; p.m = m; p.k = k; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
+  p.a = a; p.b = b; p.c = c;
+  run(&p, name);
+}
+
 /* ---------------------------------------------------------------- TRMM / TRSM ---- */
 static int diag_of_char(char ch) { ch = upper(ch); return ch == 'U' ? 1 : ch == 'N' ? 0 : -1; }   /* 1 = unit */
 static int diag_of_cblas(int d) { return d == CblasUnit ? 1 : d == CblasNonUnit ? 0 : -1; }
@@ -283,3 +337,23 @@ DEF_TRXM(strsm, "STRSM ", B200_TRSM, B200_S, 0, float, float, SC_REAL, float)
 DEF_TRXM(dtrsm, "DTRSM ", B200_TRSM, B200_D, 0, double, double, SC_REAL, double)
 DEF_TRXM(ctrsm, "CTRSM ", B200_TRSM, B200_C, 1, void, const void *, SC_CF, float)
 DEF_TRXM(ztrsm, "ZTRSM ", B200_TRSM, B200_Z, 1, void, const void *, SC_CD, double)
+
+/* GEMMT: op decoding as GEMM's (N, T, R, C; real types fold R -> N, C -> T) */
+#define DEF_GEMMT(P, NAME, DTYPE, CPLX, T, CS, CSCAL, FSCAL)                                                          \
+  B200_EXPORT void cblas_##P(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,                \
+                             enum CBLAS_TRANSPOSE TransB, blasint M, blasint K, CS alpha, const T *A, blasint lda,     \
+                             const T *B, blasint ldb, CS beta, T *C, blasint ldc) {                                    \
+    const double al[2] = CSCAL(alpha), be[2] = CSCAL(beta);                                                           \
+    gemmt_entry(NAME, DTYPE, 1, (int)Order, uplo_of_cblas((int)Uplo), op_of_cblas((int)TransA, CPLX),                  \
+                op_of_cblas((int)TransB, CPLX), M, K, al, A, lda, B, ldb, be, C, ldc);                                 \
+  }                                                                                                                   \
+  B200_EXPORT void P##_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, FSCAL *alpha, FSCAL *a,        \
+                        blasint *ldA, FSCAL *b, blasint *ldB, FSCAL *beta, FSCAL *c, blasint *ldC) {                   \
+    const double al[2] = F_##CSCAL(alpha), be[2] = F_##CSCAL(beta);                                                   \
+    gemmt_entry(NAME, DTYPE, 0, 0, uplo_of_char(*UPLO), op_of_char(*TRANSA, CPLX), op_of_char(*TRANSB, CPLX), *M, *K,  \
+                al, a, *ldA, b, *ldB, be, c, *ldC);                                                                    \
+  }
+DEF_GEMMT(sgemmt, "SGEMMT ", B200_S, 0, float, float, SC_REAL, float)
+DEF_GEMMT(dgemmt, "DGEMMT ", B200_D, 0, double, double, SC_REAL, double)
+DEF_GEMMT(cgemmt, "CGEMMT ", B200_C, 1, void, const void *, SC_CF, float)
+DEF_GEMMT(zgemmt, "ZGEMMT ", B200_Z, 1, void, const void *, SC_CD, double)

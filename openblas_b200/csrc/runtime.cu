@@ -1009,6 +1009,8 @@ B200_HIDDEN int b200_run_convert(int dir, int64_t n, const void *in, int64_t inc
   return err;
 }
 
+#include "runtime_bf16.inl"
+
 B200_HIDDEN void b200_fatal(const char *where, int err) {
   fprintf(stderr, "openblas_b200: %s failed: %s [cuda error %d]. There is no CPU fallback.\n", where,
           t_error[0] ? t_error : "unknown error", err);

@@ -126,8 +126,10 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
     return tri_recurse(w, 0, p->side ? p->n : p->m, ar, ai);
   }
 
+  /* SYRK family and GEMMT: the uplo triangle of the n x n matrix C := alpha op1(X) op2(Y) [+ second product] + beta C */
   const bool herm = p->routine == B200_HERK || p->routine == B200_HER2K;
   const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
+  const bool gemmt = p->routine == B200_GEMMT;
   const int64_t n = p->n, k = p->k;
   const bool product = k > 0 && !alpha_zero;
   if (!product) {                      /* only the triangle is scaled; beta == 1 leaves C alone */
@@ -138,10 +140,15 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
   /* first factor op(X) (rows of C), second factor op(Y)^T or op(Y)^H (columns of C):
    *   trans == 0: X is n x k, rows i0.. start at X + i0;        first N, second T (or C)
    *   trans == 1: X is k x n, rows i0.. start at X + i0 * ldx;  first T (or C), second N */
-  const int op_first = p->trans ? (herm ? B200_C_ : B200_T) : B200_N;
-  const int op_second = p->trans ? B200_N : (herm ? B200_C_ : B200_T);
-  auto at = [&](const char *x, int64_t ldx, int64_t i0) { return x + (p->trans ? (size_t)i0 * (size_t)ldx : (size_t)i0) * es; };
+  /* GEMMT (interface/gemmt.c): op1 = op(A), op2 = op(B) as given, Y = B */
+  const int op_first = gemmt ? p->trans : p->trans ? (herm ? B200_C_ : B200_T) : B200_N;
+  const int op_second = gemmt ? p->transb : p->trans ? B200_N : (herm ? B200_C_ : B200_T);
+  /* rows i0.. of op1(X) / columns j0.. of op2(Y) as GEMM operands */
+  auto at = [&](const char *x, int64_t ldx, int64_t i0) { return x + ((op_first & 1) ? (size_t)i0 * (size_t)ldx : (size_t)i0) * es; };
+  auto at2 = [&](const char *y, int64_t ldy, int64_t j0) { return y + ((op_second & 1) ? (size_t)j0 : (size_t)j0 * (size_t)ldy) * es; };
   const double ai2 = herm ? -ai : ai;  /* HER2K: the second product carries conj(alpha) */
+  const char *y1 = (two || gemmt) ? b : a;            /* second factor of the first product */
+  const int64_t ldy1 = (two || gemmt) ? ldb : lda;
 
   /* Preferred: ONE launch per product with the triangle handled inside the GEMM kernel (tiles
    * outside the triangle skipped, stores of the diagonal tiles masked): no small diagonal-block
@@ -152,7 +159,7 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
   const bool tri_gemm_ok = !(tri_env && atoi(tri_env) == 0);
   if (tri_gemm_ok) {
     const int tri = p->uplo ? 1 : 2;
-    cudaError_t e = gemm_on_device(p->dtype, op_first, op_second, n, n, k, ar, ai, a, lda, two ? b : a, two ? ldb : lda, br, bi, c, ldc, s, tri);
+    cudaError_t e = gemm_on_device(p->dtype, op_first, op_second, n, n, k, ar, ai, a, lda, y1, ldy1, br, bi, c, ldc, s, tri);
     if (e == cudaSuccess) {
       if (two) CK(gemm_on_device(p->dtype, op_first, op_second, n, n, k, ar, ai2, b, ldb, a, lda, 1.0, 0.0, c, ldc, s, tri));
       if (herm) CK(launch_real_diagonal(p->dtype, n, c, ldc, s));
@@ -169,15 +176,13 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
     const int64_t i0 = p->uplo ? j0 + jb : 0, mr = p->uplo ? n - j0 - jb : j0;
     char *c_rect = c + ((size_t)i0 + (size_t)j0 * (size_t)ldc) * es;
     if (mr > 0) {
-      CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai, at(a, lda, i0), lda, at(two ? b : a, two ? ldb : lda, j0),
-                        two ? ldb : lda, br, bi, c_rect, ldc, s));
-      if (two) CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai2, at(b, ldb, i0), ldb, at(a, lda, j0), lda, 1.0, 0.0,
+      CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai, at(a, lda, i0), lda, at2(y1, ldy1, j0), ldy1, br, bi, c_rect, ldc, s));
+      if (two) CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai2, at(b, ldb, i0), ldb, at2(a, lda, j0), lda, 1.0, 0.0,
                                  c_rect, ldc, s));
     }
     /* diagonal block through the scratch tile */
-    CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai, at(a, lda, j0), lda, at(two ? b : a, two ? ldb : lda, j0),
-                      two ? ldb : lda, 0.0, 0.0, scratch, ldt, s));
-    if (two) CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai2, at(b, ldb, j0), ldb, at(a, lda, j0), lda, 1.0, 0.0,
+    CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai, at(a, lda, j0), lda, at2(y1, ldy1, j0), ldy1, 0.0, 0.0, scratch, ldt, s));
+    if (two) CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai2, at(b, ldb, j0), ldb, at2(a, lda, j0), lda, 1.0, 0.0,
                                scratch, ldt, s));
     CK(launch_tri_merge(p->dtype, p->uplo, herm, jb, scratch, ldt, br, bi, c + ((size_t)j0 + (size_t)j0 * (size_t)ldc) * es, ldc, s));
   }
@@ -189,6 +194,7 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   const bool trxm = p->routine == B200_TRMM || p->routine == B200_TRSM;
   const bool symm = p->routine == B200_SYMM || p->routine == B200_HEMM;
   const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
+  const bool gemmt = p->routine == B200_GEMMT;
   const bool alpha_zero = p->alpha[0] == 0.0 && p->alpha[1] == 0.0;
   const bool beta_one = p->beta[0] == 1.0 && p->beta[1] == 0.0, beta_zero = p->beta[0] == 0.0 && p->beta[1] == 0.0;
   const bool product = !alpha_zero && (symm || trxm || p->k > 0);
@@ -200,12 +206,13 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
     const int64_t ka = p->side ? p->n : p->m;
     A.rows = A.cols = ka; B.rows = p->m; B.cols = p->n;
   } else {
-    A.rows = p->trans ? p->k : p->n; A.cols = p->trans ? p->n : p->k;
+    A.rows = (p->trans & 1) ? p->k : p->n; A.cols = (p->trans & 1) ? p->n : p->k;
     B.rows = A.rows; B.cols = A.cols;
+    if (gemmt) { B.rows = (p->transb & 1) ? p->n : p->k; B.cols = (p->transb & 1) ? p->k : p->n; }
   }
   C.rows = p->m; C.cols = p->n;
   A.ld_user = p->lda; B.ld_user = p->ldb; C.ld_user = p->ldc;
-  const bool use_b = product && (symm || two);
+  const bool use_b = product && (symm || two || gemmt);
   A.kind = product ? classify(p->a) : PTR_DEVICE;
   B.kind = use_b ? classify(p->b) : PTR_DEVICE;
   C.kind = classify(p->c);

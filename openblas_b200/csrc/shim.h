@@ -52,7 +52,7 @@ B200_HIDDEN int b200_run_batch(const b200_problem *p, int64_t count);
 
 /* One normalised (column-major) problem of the symmetric level-3 family; the
  * analogue of blas_arg_t as interface/symm.c / syrk.c / syr2k.c fill it. */
-enum b200_l3_routine { B200_SYMM = 0, B200_HEMM, B200_SYRK, B200_HERK, B200_SYR2K, B200_HER2K, B200_TRMM, B200_TRSM };
+enum b200_l3_routine { B200_SYMM = 0, B200_HEMM, B200_SYRK, B200_HERK, B200_SYR2K, B200_HER2K, B200_TRMM, B200_TRSM, B200_GEMMT };
 typedef struct b200_l3_problem {
   int routine;          /* enum b200_l3_routine */
   int dtype;            /* enum b200_dtype (S, D, C, Z) */
@@ -60,6 +60,7 @@ typedef struct b200_l3_problem {
   int uplo;             /* 0 = upper, 1 = lower: triangle of A (SYMM/HEMM) or of C (the others) */
   int trans;            /* SYRK family: 0 = A (and B) are n x k, 1 = k x n (T, or C for HERK/HER2K);
                            TRMM/TRSM: enum b200_trans of op(A) */
+  int transb;           /* GEMMT only: enum b200_trans of op(B) (trans holds op(A)'s); C is n x n, op(A) n x k, op(B) k x n */
   int unit;             /* TRMM/TRSM: 1 = unit diagonal (never read) */
   int64_t m, n, k;      /* SYMM/HEMM: C is m x n; SYRK family: C is n x n */
   int64_t lda, ldb, ldc;
@@ -71,6 +72,12 @@ typedef struct b200_l3_problem {
 
 /* Synchronous solve; pointers may be host or device (runtime.cu). */
 B200_HIDDEN int b200_run_level3(const b200_l3_problem *p);
+
+/* SBGEMV (interface/sbgemv.c): y := alpha * op(A) x + beta * y, A m x n bf16 column-major, x bf16, y fp32; x and y
+ * point at the LOGICAL first element (the interface moved them for negative increments).  SBDOT likewise. */
+B200_HIDDEN int b200_run_sbgemv(int trans, int64_t m, int64_t n, float alpha, const void *a, int64_t lda, const void *x,
+                                int64_t incx, float beta, void *y, int64_t incy);
+B200_HIDDEN int b200_run_sbdot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, float *result);
 
 /* bf16 <-> fp32/fp64 conversion on the device, strided host or device arrays.
  * dir: 0 = float->bf16, 1 = double->bf16, 2 = bf16->float, 3 = bf16->double */

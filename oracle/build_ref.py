@@ -125,16 +125,36 @@ def build_ctest(lib_dir, base):
         exe = os.path.join(cdir, f"x{p}cblat3")
         run([CC, "-o", exe] + objs + [stub_c, f"-L{lib_dir}", "-lopenblas_b200",
                                        f"-Wl,-rpath,$ORIGIN/../../../openblas_b200/lib", "-lm", "-lpthread"])
-    # the SBGEMM-vs-SGEMM comparison program of the reference (test/compare_sgemm_sbgemm.c)
+    # the GEMM3M flavour of the complex drivers (ctest/Makefile:56,64,168-176,312-314,340-342): c_?blat3c_3m.c +
+    # c_?blas3_3m.c + c_?3chke_3m.c, input files ?in3_3m
+    for p in "cz":
+        objs = []
+        for f in [f"c_{p}blat3c_3m.c", f"c_{p}blas3_3m.c", f"c_{p}3chke_3m.c", "auxiliary.c", "c_xerbla.c", "constant.c"]:
+            o = os.path.join(cdir, f"{p}3m_{f[:-2]}.o")
+            extra = ["-DDOUBLE"] if p == "z" else []
+            extra += ["-DCOMPLEX"]
+            run([CC] + flags + extra + ["-c", os.path.join(src, f), "-o", o])
+            objs.append(o)
+        shutil.copyfile(os.path.join(src, f"{p}in3_3m"), os.path.join(cdir, f"{p}in3_3m"))
+        exe = os.path.join(cdir, f"x{p}cblat3_3m")
+        run([CC, "-o", exe] + objs + [f"-L{lib_dir}", "-lopenblas_b200", f"-Wl,-rpath,$ORIGIN/../../../openblas_b200/lib", "-lm", "-lpthread"])
+    # the SBGEMM-vs-SGEMM comparison program of the reference (test/compare_sgemm_sbgemm.c).  Its second half
+    # compares SBGEMV with SGEMV; SGEMV is not on the GEMM path and not in this library, so the harness gets a
+    # plain netlib-semantics sgemv_ of its own (the program only uses it as the fp32 yardstick, tolerance 1.0).
     exe = os.path.join(cdir, "test_sbgemm")
     gemv_stub = os.path.join(cdir, "stubs_gemv.c")
     open(gemv_stub, "w").write(
-        "/* TEST INFRASTRUCTURE: the second half of compare_sgemm_sbgemm.c tests SBGEMV, which is not on\n"
-        " * the GEMM path.  Reaching it means the SBGEMM half finished with ret == 0 (the program\n"
-        " * returns early with 'FATAL ERROR SBGEMM' otherwise, compare_sgemm_sbgemm.c:194-197). */\n"
-        "#include <stdio.h>\n#include <stdlib.h>\n"
-        "void sgemv_(void) { printf(\"SBGEMM half PASSED; SBGEMV is outside this library\\n\"); exit(0); }\n"
-        "void sbgemv_(void) { sgemv_(); }\n")
+        "/* TEST INFRASTRUCTURE: fp32 yardstick for the SBGEMV half of compare_sgemm_sbgemm.c (reference/sgemvf.f semantics,\n"
+        " * positive increments only, as the program calls it).  sbgemv_ itself comes from libopenblas_b200.so. */\n"
+        "void sgemv_(char *trans, int *m, int *n, float *alpha, float *a, int *lda, float *x, int *incx, float *beta, float *y, int *incy) {\n"
+        "  int t = (*trans == 'T' || *trans == 't' || *trans == 'C' || *trans == 'c');\n"
+        "  int leny = t ? *n : *m, lenx = t ? *m : *n;\n"
+        "  for (int i = 0; i < leny; i++) {\n"
+        "    float acc = 0.f;\n"
+        "    for (int j = 0; j < lenx; j++) acc += (t ? a[j + (long)i * *lda] : a[i + (long)j * *lda]) * x[(long)j * *incx];\n"
+        "    y[(long)i * *incy] = *alpha * acc + (*beta == 0.f ? 0.f : *beta * y[(long)i * *incy]);\n"
+        "  }\n"
+        "}\n")
     run([CC] + base + ["-DBFLOAT16", "-w", os.path.join(REF, "test", "compare_sgemm_sbgemm.c"), gemv_stub, "-o", exe,
                        f"-L{lib_dir}", "-lopenblas_b200", f"-Wl,-rpath,$ORIGIN/../../../openblas_b200/lib",
                        "-lm", "-lpthread"])

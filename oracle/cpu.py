@@ -86,6 +86,18 @@ class Oracle:
         L.oracle_check_rankk.restype = C.c_int
         L.oracle_check_rankk.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_long] * 5 + [C.c_int]
         L.oracle_bf16to.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.oracle_gemmt.restype = C.c_int
+        L.oracle_gemmt.argtypes = [C.c_int] * 4 + [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                                   C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_check_gemmt.restype = C.c_int
+        L.oracle_check_gemmt.argtypes = [C.c_int] * 4 + [C.c_long] * 5 + [C.c_int]
+        L.oracle_sbgemv.restype = C.c_int
+        L.oracle_sbgemv.argtypes = [C.c_int, C.c_long, C.c_long, C.c_float, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_float,
+                                    C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_sbdot.restype = C.c_double
+        L.oracle_sbdot.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_check_sbgemv.restype = C.c_int
+        L.oracle_check_sbgemv.argtypes = [C.c_int] + [C.c_long] * 5 + [C.c_int]
 
     def gemm(self, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, q=0, unroll_m=0, small=False):
         """In-place on c (column-major storage, numpy arrays of the dtype's element type)."""
@@ -148,6 +160,31 @@ class Oracle:
 
     def check_rankk(self, two, uplo, trans, n, k, lda, ldb, ldc, ok):
         return self.lib.oracle_check_rankk(two, uplo, trans, n, k, lda, ldb, ldc, ok)
+
+    def gemmt(self, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """?GEMMT in place on the uplo triangle of c (column-major); returns the m x m gauge (0 outside the triangle)."""
+        al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+        g = np.zeros((max(m, 1), max(m, 1)), dtype=np.float64)
+        assert self.lib.oracle_gemmt(dtype, uplo, ta, tb, m, k, _ptr(al), _ptr(a), lda, _ptr(b), ldb, _ptr(be), _ptr(c), ldc, _ptr(g)) == 0
+        return g
+
+    def check_gemmt(self, rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, ok):
+        return self.lib.oracle_check_gemmt(rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, ok)
+
+    def sbgemv(self, trans, m, n, alpha, a, lda, x, incx, beta, y, incy):
+        """SBGEMV in place on y; x and y are the arrays as the CALLER holds them (lowest address first; a negative
+        increment walks from the far end, as in the interface).  Returns the gauge per output."""
+        lenx, leny = (m, n) if trans else (n, m)
+        g = np.zeros(max(leny, 1), dtype=np.float64)
+        assert self.lib.oracle_sbgemv(trans, m, n, alpha, _ptr(a), lda, _ptr(x), incx, beta, _ptr(y), incy, _ptr(g)) == 0
+        return g
+
+    def sbdot(self, n, x, incx, y, incy):
+        g = C.c_double(0.0)
+        return self.lib.oracle_sbdot(n, _ptr(x), incx, _ptr(y), incy, C.byref(g)), g.value
+
+    def check_sbgemv(self, trans, m, n, lda, incx, incy, ok):
+        return self.lib.oracle_check_sbgemv(trans, m, n, lda, incx, incy, ok)
 
     def tobf16(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -231,6 +268,51 @@ def call_trxm(lib, dtype, solve, side, uplo, trans, unit, m, n, alpha, a, lda, b
     fn(C.c_char_p(b"LR"[side:side + 1]), C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(b"NTRC"[trans:trans + 1]),
        C.c_char_p(b"NU"[unit:unit + 1]), i(m), i(n), _ptr(al), _ptr(a), i(lda), _ptr(b), i(ldb))
     return b
+
+
+def call_gemmt(lib, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c, ldc, cblas=False, rowmajor=False):
+    """?gemmt_ (common_interface.h:506-513) or cblas_?gemmt (cblas.h:311-318) of any library."""
+    al, be = scalar_bytes(dtype, alpha), scalar_bytes(dtype, beta)
+    P = lambda v: C.c_void_p(v) if isinstance(v, int) else _ptr(v)        # device addresses come as ints
+    if cblas:
+        fn = getattr(lib, "cblas_" + DTYPE_NAMES[dtype] + "gemmt")
+        if dtype in (CX, Z):
+            sa, sb = _ptr(al), _ptr(be)
+        else:
+            t = C.c_double if dtype == D else C.c_float
+            sa, sb = t(float(np.real(alpha))), t(float(np.real(beta)))
+        fn(101 if rowmajor else 102, 121 if uplo == 0 else 122, CBLAS_TRANS[ta], CBLAS_TRANS[tb], C.c_int(m), C.c_int(k), sa,
+           P(a), C.c_int(lda), P(b), C.c_int(ldb), sb, P(c), C.c_int(ldc))
+        return c
+    fn = getattr(lib, DTYPE_NAMES[dtype] + "gemmt_")
+    i = lambda v: C.byref(C.c_int(int(v)))
+    fn(C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(TRANS_CHAR[ta].encode()), C.c_char_p(TRANS_CHAR[tb].encode()), i(m), i(k),
+       _ptr(al), P(a), i(lda), P(b), i(ldb), _ptr(be), P(c), i(ldc))
+    return c
+
+
+def call_sbgemv(lib, trans, m, n, alpha, a, lda, x, incx, beta, y, incy, cblas=False, rowmajor=False):
+    """sbgemv_ (common_interface.h:258) or cblas_sbgemv (cblas.h:442) of any library; a, x, y: addresses or arrays."""
+    P = lambda v: C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+    if cblas:
+        lib.cblas_sbgemv(101 if rowmajor else 102, CBLAS_TRANS[trans], C.c_int(m), C.c_int(n), C.c_float(alpha), P(a), C.c_int(lda),
+                         P(x), C.c_int(incx), C.c_float(beta), P(y), C.c_int(incy))
+        return y
+    i = lambda v: C.byref(C.c_int(int(v)))
+    lib.sbgemv_(C.c_char_p(TRANS_CHAR[trans].encode()), i(m), i(n), C.byref(C.c_float(alpha)), P(a), i(lda), P(x), i(incx),
+                C.byref(C.c_float(beta)), P(y), i(incy))
+    return y
+
+
+def call_sbdot(lib, n, x, incx, y, incy, cblas=False):
+    """sbdot_ (common_interface.h:62) or cblas_sbdot (cblas.h:441) of any library."""
+    P = lambda v: C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+    if cblas:
+        lib.cblas_sbdot.restype = C.c_float
+        return float(lib.cblas_sbdot(C.c_int(n), P(x), C.c_int(incx), P(y), C.c_int(incy)))
+    lib.sbdot_.restype = C.c_float
+    i = lambda v: C.byref(C.c_int(int(v)))
+    return float(lib.sbdot_(i(n), P(x), i(incx), P(y), i(incy)))
 
 
 class Reference:

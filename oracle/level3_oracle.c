@@ -320,3 +320,160 @@ int oracle_check_trxm(int side, int uplo, int trans, int unit, long m, long n, l
   if (side < 0) info = 1;
   return info;
 }
+
+/* ---- ?GEMMT: the uplo triangle of the m x m matrix  C := alpha * op(A) * op(B) + beta * C  ---------------
+ * interface/gemmt.c:474-680 does this column by column with GEMV: column i of the triangle gets
+ * SCAL_K(beta) (beta == 0 writes zeros without reading C, beta == 1 leaves it) and then, unless alpha == 0,
+ * GEMV over the k columns / rows of op(A) restricted to the rows of the triangle.  The reference's own
+ * acceptance test (utest/test_extensions/test_dgemmt.c:56-107, ?gemmt_trusted) defines the expected result
+ * as the triangle of the GEMM result, which is what this restatement computes: one dot product per element
+ * in the working precision.  Unlike the reference (gemmt.c:466-476 conjugates B IN PLACE for transb = R / C
+ * and never undoes it), B is not modified.  PINNED BY BOUND against oracle/_ref/generic (?gemmt_ and
+ * cblas_?gemmt compiled from interface/gemmt.c) in tests/test_oracle_pin.py.
+ * transa / transb: 0 N, 1 T, 2 conj, 3 conj-trans (real types fold 2 -> 0, 3 -> 1). */
+#define GEN_GEMMT(T, SFX)                                                                                   \
+  static void gemmt_##SFX(int cplx, int uplo, int ta, int tb, long m, long k, const T *alpha, const T *a, long lda, \
+                          const T *b, long ldb, const T *beta, T *c, long ldc, double *gauge) {              \
+    cx_##SFX al = ld_##SFX(alpha, 0, cplx), be = ld_##SFX(beta, 0, cplx);                                   \
+    int product = k > 0 && !(al.re == 0 && al.im == 0);                                                     \
+    int beta_zero = be.re == 0 && be.im == 0, beta_one = be.re == 1 && be.im == 0;                          \
+    if (gauge) for (long x = 0; x < m * m; x++) gauge[x] = 0;                                               \
+    if (!product && beta_one) return;                                                                       \
+    for (long j = 0; j < m; j++)                                                                            \
+      for (long i = uplo ? j : 0; i < (uplo ? m : j + 1); i++) {                                            \
+        cx_##SFX acc = {0, 0};                                                                              \
+        double g = 0;                                                                                       \
+        if (product)                                                                                        \
+          for (long l = 0; l < k; l++) {                                                                    \
+            cx_##SFX x = cj_##SFX(ld_##SFX(a, (ta & 1) ? l + i * lda : i + l * lda, cplx), ta & 2);         \
+            cx_##SFX y = cj_##SFX(ld_##SFX(b, (tb & 1) ? j + l * ldb : l + j * ldb, cplx), tb & 2);         \
+            acc = add_##SFX(acc, mul_##SFX(x, y));                                                          \
+            g += a1_##SFX(x) * a1_##SFX(y);                                                                 \
+          }                                                                                                 \
+        cx_##SFX r = mul_##SFX(al, acc);                                                                    \
+        g *= a1_##SFX(al);                                                                                  \
+        if (!beta_zero) {                                                                                   \
+          cx_##SFX c0 = ld_##SFX(c, i + j * ldc, cplx);                                                     \
+          r = add_##SFX(r, mul_##SFX(be, c0));                                                              \
+          g += a1_##SFX(be) * a1_##SFX(c0);                                                                 \
+        }                                                                                                   \
+        st_##SFX(c, i + j * ldc, cplx, r);                                                                  \
+        if (gauge) gauge[i + j * m] = g;                                                                    \
+      }                                                                                                     \
+  }
+GEN_GEMMT(float, f)
+GEN_GEMMT(double, d)
+
+int oracle_gemmt(int dtype, int uplo, int transa, int transb, long m, long k, const void *alpha, const void *a, long lda,
+                 const void *b, long ldb, const void *beta, void *c, long ldc, double *gauge) {
+  if (m <= 0) return 0;
+  int cplx = dtype == OR_C || dtype == OR_Z;
+  if (!cplx) { transa &= 1; transb &= 1; }
+  if (dtype == OR_S || dtype == OR_C)
+    gemmt_f(cplx, uplo, transa, transb, m, k, (const float *)alpha, (const float *)a, lda, (const float *)b, ldb,
+            (const float *)beta, (float *)c, ldc, gauge);
+  else if (dtype == OR_D || dtype == OR_Z)
+    gemmt_d(cplx, uplo, transa, transb, m, k, (const double *)alpha, (const double *)a, lda, (const double *)b, ldb,
+            (const double *)beta, (double *)c, ldc, gauge);
+  else return -1;
+  return 0;
+}
+
+/* interface/gemmt.c:163-186 (column-major, both ABIs): info xerbla_ gets, or `ok`.  The row-major branch
+ * (:365-389) runs the same checks on the swapped problem but reports the swapped positions: 10 for the
+ * leading dimension it calls lda (the caller's LDB), 8 for ldb (the caller's LDA), the 10 check last of the
+ * two; 3 / 2 for the trans arguments. */
+int oracle_check_gemmt(int rowmajor, int uplo, int transa, int transb, long m, long k, long lda, long ldb, long ldc, int ok) {
+  int info = ok;
+  if (!rowmajor) {
+    long nrowa = (transa & 1) ? k : m, nrowb = (transb & 1) ? m : k;
+    if (ldc < max1(m)) info = 13;
+    if (ldb < max1(nrowb)) info = 10;
+    if (lda < max1(nrowa)) info = 8;
+    if (k < 0) info = 5;
+    if (m < 0) info = 4;
+    if (transb < 0) info = 3;
+    if (transa < 0) info = 2;
+    if (uplo < 0) info = 1;
+  } else {   /* arguments as the swapped column-major problem sees them: a = B, b = A */
+    long ncola = (transa & 1) ? k : m, ncolb = (transb & 1) ? m : k;
+    if (ldc < max1(m)) info = 13;
+    if (ldb < max1(ncolb)) info = 8;
+    if (lda < max1(ncola)) info = 10;
+    if (k < 0) info = 5;
+    if (m < 0) info = 4;
+    if (transb < 0) info = 2;
+    if (transa < 0) info = 3;
+    if (uplo < 0) info = 1;
+  }
+  return info;
+}
+
+/* ---- SBGEMV / SBDOT (bf16 in, fp32 accumulate and out) ---------------------------------------------------
+ * kernel/x86_64/sbgemv_n.c:44-80, sbgemv_t.c (the C kernels every target without AVX512-BF16 runs): both
+ * operands widened to fp32 (exact), one fp32 accumulator per output walked in storage order,
+ * y = alpha * acc (beta == 0: y not read) or alpha * acc + beta * y.  interface/sbgemv.c:171-183: m == 0 or
+ * n == 0 returns, alpha == 0 only scales y by beta (beta == 1: untouched), negative increments walk from the
+ * far end.  kernel/x86_64/sbdot.c:37-58: both vectors widened to fp32, SDOT.  x and y are passed as the
+ * interface passes them to the kernel (already moved to the logical first element).
+ * PINNED against oracle/_ref/generic (sbgemv_, cblas_sbgemv, sbdot_, cblas_sbdot) in tests/test_oracle_pin.py:
+ * bit for bit on the generic target's C kernels for SBGEMV, by bound for SBDOT (the SDOT kernel accumulates in
+ * double, kernel/arm/dot.c). */
+static float bf16_widen(unsigned short v) { unsigned int u = (unsigned int)v << 16; float f; memcpy(&f, &u, 4); return f; }
+
+int oracle_sbgemv(int trans, long m, long n, float alpha, const unsigned short *a, long lda, const unsigned short *x, long incx,
+                  float beta, float *y, long incy, double *gauge) {
+  if (m <= 0 || n <= 0) return 0;
+  long lenx = trans ? m : n, leny = trans ? n : m;
+  if (incx < 0) x -= (lenx - 1) * incx;
+  if (incy < 0) y -= (leny - 1) * incy;
+  if (gauge) for (long i = 0; i < leny; i++) gauge[i] = 0;
+  if (alpha == 0.0f) {
+    if (beta != 1.0f) for (long i = 0; i < leny; i++) {
+      if (gauge) gauge[i] = fabs((double)beta) * fabs((double)y[i * incy]);
+      y[i * incy] = beta == 0.0f ? 0.0f : beta * y[i * incy];
+    }
+    return 0;
+  }
+  for (long i = 0; i < leny; i++) {
+    float acc = 0.0f;
+    double g = 0;
+    for (long j = 0; j < lenx; j++) {
+      float av = bf16_widen(trans ? a[j + i * lda] : a[i + j * lda]), xv = bf16_widen(x[j * incx]);
+      acc += av * xv;
+      g += fabs((double)av) * fabs((double)xv);
+    }
+    g *= fabs((double)alpha);
+    if (beta == 0.0f) y[i * incy] = alpha * acc;
+    else { g += fabs((double)beta) * fabs((double)y[i * incy]); y[i * incy] = alpha * acc + beta * y[i * incy]; }
+    if (gauge) gauge[i] = g;
+  }
+  return 0;
+}
+
+double oracle_sbdot(long n, const unsigned short *x, long incx, const unsigned short *y, long incy, double *gauge) {
+  if (gauge) *gauge = 0;
+  if (n <= 0) return 0.0;
+  if (incx < 0) x -= (n - 1) * incx;
+  if (incy < 0) y -= (n - 1) * incy;
+  double acc = 0, g = 0;
+  for (long i = 0; i < n; i++) {
+    double xv = bf16_widen(x[i * incx]), yv = bf16_widen(y[i * incy]);
+    acc += xv * yv;
+    g += fabs(xv) * fabs(yv);
+  }
+  if (gauge) *gauge = g;
+  return (double)(float)acc;
+}
+
+/* interface/sbgemv.c:86-92 / 130-135 (after the row-major swap of m, n and trans) */
+int oracle_check_sbgemv(int trans, long m, long n, long lda, long incx, long incy, int ok) {
+  int info = ok;
+  if (incy == 0) info = 11;
+  if (incx == 0) info = 8;
+  if (lda < max1(m)) info = 6;
+  if (n < 0) info = 3;
+  if (m < 0) info = 2;
+  if (trans < 0) info = 1;
+  return info;
+}

@@ -18,6 +18,9 @@ int oracle_gemm(int dtype, int transa, int transb, long m, long n, long k, const
 void oracle_tobf16(long n, const float *in, long inc_in, uint16_t *out, long inc_out);
 void oracle_bf16to(long n, const uint16_t *in, long inc_in, float *out, long inc_out);
 uint16_t oracle_f32_to_bf16(float f);
+int oracle_sbgemv(int trans, long m, long n, float alpha, const unsigned short *a, long lda, const unsigned short *x, long incx,
+                  float beta, float *y, long incy, double *gauge);
+double oracle_sbdot(long n, const unsigned short *x, long incx, const unsigned short *y, long incy, double *gauge);
 float oracle_bf16_to_f32(uint16_t h);
 }
 
@@ -207,6 +210,27 @@ cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff
     default: return cudaErrorNotSupported;
   }
   count_launch(solve ? "sim_tri_block_solve" : "sim_tri_block_multiply");
+  return cudaSuccess;
+}
+
+/* SBGEMV / SBDOT: the oracle on the staged operands.  The launchers get x and y at their LOGICAL first element;
+ * the oracle, like the interface, takes the lowest address and moves it itself -- undo the move for it. */
+size_t sbgemv_workspace_bytes(int, int64_t, int64_t) { return 256; }
+cudaError_t launch_sbgemv(int trans, int64_t m, int64_t n, float alpha, const void *a, int64_t lda, const void *x, int64_t incx, float beta,
+                          void *y, int64_t incy, void *, cudaStream_t) {
+  const int64_t lenx = trans ? m : n, leny = trans ? n : m;
+  const unsigned short *x0 = (const unsigned short *)x + (incx < 0 ? (lenx - 1) * incx : 0);
+  float *y0 = (float *)y + (incy < 0 ? (leny - 1) * incy : 0);
+  oracle_sbgemv(trans, m, n, alpha, (const unsigned short *)a, lda, x0, incx, beta, y0, incy, nullptr);
+  count_launch("sim_sbgemv");
+  return cudaSuccess;
+}
+size_t sbdot_workspace_bytes() { return 256; }
+cudaError_t launch_sbdot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, void *, float *result, cudaStream_t) {
+  const unsigned short *x0 = (const unsigned short *)x + (incx < 0 ? (n - 1) * incx : 0);
+  const unsigned short *y0 = (const unsigned short *)y + (incy < 0 ? (n - 1) * incy : 0);
+  *result = (float)oracle_sbdot(n, x0, incx, y0, incy, nullptr);
+  count_launch("sim_sbdot");
   return cudaSuccess;
 }
 

@@ -528,3 +528,61 @@ def test_randomised_level3_stress(sim, oracle, seed, monkeypatch):
                 a[off] *= min(1.0, 4.0 / ka)
             b0 = L.operand(rng, dtype, n, m + 2)
             L.check_trxm(oracle, sim, (dtype, solve, side, uplo, trans, unit, m, n, ka + 1, m + 2, alpha), a, b0)
+
+
+def test_gemmt_sbgemv_sbdot_golden_vectors_through_the_host_path(sim, oracle):
+    """The reference-generated cases of tests/golden/f_rows_golden.npz through interface_level3.c / interface_gemm.c
+    and the staging of runtime_level3.inl / runtime_bf16.inl: flag decoding, the row-major swap, operand
+    shapes and offsets, increments (gathered / scattered on the host), alpha == 0 and beta == 0 paths."""
+    import test_f_rows_pin as F
+    g = np.load(os.path.join(ROOT, "tests", "golden", "f_rows_golden.npz"))
+    for i in range(int(g["gemmt_count"][0])):
+        key = f"gemmt{i}"
+        dtype, uplo, ta, tb, m, k, lda, ldb, ldc, cblas, rowmajor = F.colmajor_problem(g[key + "_meta"])
+        cplx = dtype in (cpu.CX, cpu.Z)
+        alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
+        a, b, c0 = g[key + "_a"], g[key + "_b"], g[key + "_c0"]
+        got = c0.copy()
+        cpu.call_gemmt(sim, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, got, ldc, cblas=bool(cblas), rowmajor=bool(rowmajor))
+        assert np.array_equal(a, g[key + "_a"]) and np.array_equal(b, g[key + "_b"])         # inputs are const here
+        want, gauge, mask = F.gemmt_expected(oracle, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c0, ldc, rowmajor)
+        F.check_gemmt(dtype, m, k, ldc, got, want, gauge, mask, c0, key)                    # against the restatement
+        F.check_gemmt(dtype, m, k, ldc, got, g[key + "_c"], gauge, mask, c0, key + " vs reference")
+    for i in range(int(g["sbgemv_count"][0])):
+        key = f"sbgemv{i}"
+        trans, m, n, lda, incx, incy = (int(v) for v in g[key + "_meta"])
+        alpha, beta = (float(v) for v in g[key + "_ab"])
+        for cblas in (False, True):
+            y = g[key + "_y0"].copy()
+            cpu.call_sbgemv(sim, trans, m, n, alpha, g[key + "_a"], lda, g[key + "_x"], incx, beta, y, incy, cblas=cblas)
+            assert np.array_equal(y.view(np.uint32), g[key + "_y"].view(np.uint32)), (key, cblas)   # stand-in kernel = oracle: bit for bit
+    for i in range(int(g["sbdot_count"][0])):
+        key = f"sbdot{i}"
+        n, incx, incy = (int(v) for v in g[key + "_meta"])
+        for cblas in (False, True):
+            assert np.float32(cpu.call_sbdot(sim, n, g[key + "_x"], incx, g[key + "_y"], incy, cblas=cblas)) == g[key + "_d"][0], (key, cblas)
+
+
+def test_gemmt_block_column_scheme_and_device_operands(sim, oracle, monkeypatch):
+    """GEMMT through the block-column fallback (B200_RANKK_TRI=0) at a size that crosses block boundaries, host and
+    "device" operands, NaN outside the triangle."""
+    import test_f_rows_pin as F
+    rng = np.random.default_rng(12)
+    for tri_env in ("1", "0"):
+        monkeypatch.setenv("B200_RANKK_TRI", tri_env)
+        for dtype in (cpu.D, cpu.CX):
+            cplx = dtype == cpu.CX
+            for uplo in (0, 1):
+                for ta, tb in ((0, 0), (1, 0), (0, 1), (1, 1)) + (((3, 2), (2, 3)) if cplx else ()):
+                    m, k = 150, 37
+                    ra, ca = (k, m) if ta & 1 else (m, k)
+                    rb, cb = (m, k) if tb & 1 else (k, m)
+                    lda, ldb, ldc = ra + 3, rb + 1, m + 2
+                    a, b, c0 = F.operand(rng, dtype, ca, lda), F.operand(rng, dtype, cb, ldb), F.operand(rng, dtype, m, ldc)
+                    mask = F.tri_mask(m, ldc, uplo)
+                    c0[~mask] = np.nan
+                    alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
+                    got = c0.copy()
+                    cpu.call_gemmt(sim, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, got, ldc)
+                    want, gauge, mk = F.gemmt_expected(oracle, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c0, ldc, False)
+                    F.check_gemmt(dtype, m, k, ldc, got, want, gauge, mk, c0, (tri_env, dtype, uplo, ta, tb))
