@@ -290,9 +290,10 @@ def run_gpu(args):
             return torch.view_as_complex(r)
         return (torch.rand((cols, rows), generator=gen, device=dev, dtype=torch.float32 if t == torch.bfloat16 else t) - 0.5).to(t)
 
-    grid = summa.make_grid(world, rank) if world > 1 else None
     launches0 = ob.cblas.launch_count()
     stream = torch.cuda.current_stream(dev)
+    cs = sm = None
+    ri = cj = None
     if world == 1:
         a, b = rand(k, m, tdt), rand(n, k, tdt)
         c = torch.empty((n, m), dtype=odt, device=dev)
@@ -300,12 +301,32 @@ def run_gpu(args):
         parallelism, launches_per_step = "1 GPU", 1
     else:
         nb = args.nb
-        sm = summa.Summa(grid, m, n, k, nb, tdt, dev,
-                         lambda mm, nn, kk, al, A, lda, B, ldb, be, C, ldc, st: ob.cblas.gemm_device(code, 0, 0, mm, nn, kk, al, A, lda, B, ldb, be, C, ldc, st))
-        a, b = rand(sm.ka_loc, sm.m_loc, tdt), rand(sm.n_loc, sm.kb_loc, tdt)
-        c = torch.empty((sm.n_loc, sm.m_loc), dtype=odt, device=dev)
-        step = lambda: sm.run(1.0, a, b, 0.0, c)
-        parallelism, launches_per_step = f"summa {grid.P}x{grid.Q} block-cyclic nb={nb}", len(sm.steps)
+        P, Q = summa.grid_shape(world)
+        p_, q_ = rank // Q, rank % Q
+        # hashed global matrices: every rank can regenerate any row of A / column of B, which is what the sampled
+        # long-double check of its C block needs (no communication, nothing of it inside the timed region)
+        idx = lambda nn, i, np_: torch.tensor(summa.local_index_map(nn, nb, i, np_), dtype=torch.int64, device=dev)
+        ri, cj, ka_i, kb_i = idx(m, p_, P), idx(n, q_, Q), idx(k, q_, Q), idx(k, p_, P)
+
+        def hashed(tag, gi, gj):
+            if tdt.is_complex:
+                return torch.complex(summa.hashed_entries(tag, gi, gj), summa.hashed_entries(tag + 10, gi, gj)).to(tdt)
+            return summa.hashed_entries(tag, gi, gj).to(tdt)
+        a, b = hashed(1, ri, ka_i), hashed(2, kb_i, cj)
+        m_loc, n_loc, ka_loc, kb_loc = ri.numel(), cj.numel(), ka_i.numel(), kb_i.numel()
+        c = torch.empty((n_loc, m_loc), dtype=odt, device=dev)
+        torch.cuda.empty_cache()
+        if args.summa == "c":
+            cs = summa.CSumma(world, rank, dev)
+            step = lambda: cs.gemm(code, m, n, k, nb, 1.0, a, max(1, m_loc), b, max(1, kb_loc), 0.0, c, max(1, m_loc), stream.cuda_stream)
+            parallelism = f"{cs.describe()}; nb={nb}; b200_summa_gemm (csrc/summa.cu), one process per GPU"
+        else:
+            grid = summa.make_grid(world, rank)
+            sm = summa.Summa(grid, m, n, k, nb, tdt, dev,
+                             lambda mm, nn, kk, al, A, lda, B, ldb, be, C, ldc, st: ob.cblas.gemm_device(code, 0, 0, mm, nn, kk, al, A, lda, B, ldb, be, C, ldc, st))
+            step = lambda: sm.run(1.0, a, b, 0.0, c)
+            parallelism = f"summa.py {P}x{Q} block-cyclic nb={nb}: NCCL panel broadcasts (torch.distributed) + b200_gemm_async"
+        launches_per_step = (k + nb - 1) // nb
 
     def barrier():
         if world > 1:
@@ -321,6 +342,7 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches0 = ob.cblas.launch_count()              # kernels enqueued inside the timed region only
     e0.record(stream)
     for i in range(args.steps):
         kern_ev[i][0].record(stream)
@@ -348,15 +370,47 @@ def run_gpu(args):
     # pieces, the SUMMA sweep, D2H of the local C piece (all ranks take part, so it runs before the
     # rank-0-only reporting)
     e2e_multi = None
+    parity_multi = None
+    if world > 1:
+        # sampled long-double check of this rank's C block (outside every timed region), worst ratio over all ranks
+        import numpy as np
+        worst, samples = 0.0, 0
+        if ri.numel() and cj.numel():
+            gsel = torch.Generator(); gsel.manual_seed(100 + rank)
+            allk = torch.arange(k, dtype=torch.int64, device=dev)
+            eps = 2.0 ** -52 if dtype in ("d", "z") else 2.0 ** -23
+            ldt = np.clongdouble if tdt.is_complex else np.longdouble
+            for _ in range(16):
+                il, jl = int(torch.randint(0, ri.numel(), (1,), generator=gsel)), int(torch.randint(0, cj.numel(), (1,), generator=gsel))
+                ar = hashed(1, ri[il:il + 1], allk)[:, 0].cpu().numpy().astype(ldt)
+                bc = hashed(2, allk, cj[jl:jl + 1])[0, :].cpu().numpy().astype(ldt)
+                ref = np.dot(ar, bc)
+                gauge = float(np.dot(np.abs(ar), np.abs(bc)))
+                worst = max(worst, float(abs(ldt(c[jl, il].item()) - ref)) / (k * eps * gauge))
+                samples += 1
+        w = torch.tensor([worst], device=dev, dtype=torch.float64)
+        ns = torch.tensor([float(samples)], device=dev, dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX); dist.all_reduce(ns)
+        parity_multi = {"worst_ratio": float(w.item()), "samples": int(ns.item()), "ranks": world,
+                        "bound": "|C - C_ref| <= 2 * k * eps * (|A||B|) per entry; C_ref = long-double dot products of regenerated global rows / columns, 16 entries of every rank's block",
+                        "ok": float(w.item()) <= 2.0}
     if world > 1 and not args.no_e2e:
+        # end to end: every rank's shards start in pinned HOST memory and C ends there.  The library's driver takes the
+        # host pointers itself: uploads go straight into the panel windows in k order, the products start as soon as
+        # the first panels have landed everywhere, the last update of C comes back strip by strip.
         ha, hb = a.cpu().pin_memory(), b.cpu().pin_memory()
         hc = torch.empty(c.shape, dtype=c.dtype).pin_memory()
-        da, db, dc = torch.empty_like(a), torch.empty_like(b), torch.empty_like(c)
+        if cs is not None:
+            e2e_step = lambda: cs.gemm(code, m, n, k, args.nb, 1.0, ha, max(1, m_loc), hb, max(1, kb_loc), 0.0, hc, max(1, m_loc), stream.cuda_stream)
+            api = "per rank: b200_summa_gemm on pinned HOST shards of A, B and C (synchronous)"
+        else:
+            da, db, dc = torch.empty_like(a), torch.empty_like(b), torch.empty_like(c)
 
-        def e2e_step():
-            da.copy_(ha, non_blocking=True); db.copy_(hb, non_blocking=True)
-            sm.run(1.0, da, db, 0.0, dc)
-            hc.copy_(dc, non_blocking=True)
+            def e2e_step():
+                da.copy_(ha, non_blocking=True); db.copy_(hb, non_blocking=True)
+                sm.run(1.0, da, db, 0.0, dc)
+                hc.copy_(dc, non_blocking=True)
+            api = "per rank: pinned host shards -> device, openblas_b200.summa.Summa.run (local product b200_gemm_async), C shard -> pinned host"
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -369,10 +423,10 @@ def run_gpu(args):
         bytes_in = torch.tensor([float(ha.numel() * ha.element_size() + hb.numel() * hb.element_size())], device=dev, dtype=torch.float64)
         bytes_out = torch.tensor([float(hc.numel() * hc.element_size())], device=dev, dtype=torch.float64)
         dist.all_reduce(bytes_in); dist.all_reduce(bytes_out)
+        diff = float((hc.to(dev) - c).abs().max()) if c.numel() else 0.0       # the host-path result equals the device-path result
         e2e_multi = {"value": flops_step / float(dt_e.item()) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(bytes_in.item()),
-                     "d2h_bytes_per_step": int(bytes_out.item()), "ms_per_step": float(dt_e.item()) * 1e3, "steps": nst,
-                     "api": "per rank: pinned host shards -> device, openblas_b200.summa.Summa.run (local product b200_gemm_async), C shard -> pinned host",
-                     "result_checksum": float(hc[::97, ::89].double().sum())}
+                     "d2h_bytes_per_step": int(bytes_out.item()), "ms_per_step": float(dt_e.item()) * 1e3, "steps": nst, "api": api,
+                     "max_abs_diff_vs_device_path_rank0": diff, "result_checksum": float(hc[::97, ::89].double().sum())}
     out = None
     if rank == 0:
         e2e = None
@@ -381,7 +435,7 @@ def run_gpu(args):
         elif world > 1:
             e2e = e2e_multi
         cpu_b = cpu_baseline(dtype) if (world == 1 and not args.no_cpu) else None
-        parity = sampled_parity(torch, dtype, 0, 0, m, n, k, a, m, b, k, c, m) if world == 1 else None
+        parity = sampled_parity(torch, dtype, 0, 0, m, n, k, a, m, b, k, c, m) if world == 1 else parity_multi
         extra = run_extras(ob, torch, dev, stream, args) if (world == 1 and not args.no_extras) else None
         achieved = (real_flops_launch / (kern_ms_avg * 1e-3) / 1e12) if world == 1 else (FLOP_FACTOR[dtype] * m * n * k / world / (total_ms / args.steps * 1e-3) / 1e12)
         out = {
@@ -410,6 +464,8 @@ def run_gpu(args):
             out["e2e"] = e2e
     if world > 1:
         dist.barrier()
+        if cs is not None:
+            cs.close()
         dist.destroy_process_group()
     if out:
         print(json.dumps(out))
@@ -704,7 +760,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="d", choices=list(DT))
     ap.add_argument("--m", type=int, default=0); ap.add_argument("--n", type=int, default=0); ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--nb", type=int, default=2048, help="SUMMA distribution block / panel width")
+    ap.add_argument("--nb", type=int, default=4096, help="SUMMA distribution block / panel width")
+    ap.add_argument("--summa", default="c", choices=["c", "py"], help="N > 1: the library's own driver (csrc/summa.cu) or its Python mirror over torch.distributed broadcasts")
     ap.add_argument("--ref-n", type=int, default=0, help="reference arm: force an n^3 sample (default: the GPU arm's workload, halved only if it cannot fit --ref-budget)")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="reference arm: seconds the (steps + warmup) calls may take")
     ap.add_argument("--e2e-steps", type=int, default=2)

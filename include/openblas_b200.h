@@ -292,6 +292,32 @@ void sbdtobf16_(blasint *n, double *in, blasint *incin, bfloat16 *out, blasint *
 void sbf16tos_(blasint *n, bfloat16 *in, blasint *incin, float *out, blasint *incout);
 void dbf16tod_(blasint *n, bfloat16 *in, blasint *incin, double *out, blasint *incout);
 
+/* ---- multi-GPU: 2-D block-cyclic SUMMA over a P x Q grid of processes, one GPU each (csrc/summa.cu).
+ *      Replaces the reference's threaded level-3 driver: driver/level3/level3_thread.c:219-532 (inner_thread: every
+ *      worker packs its share once, announces it through job[].working flags, the others consume it, double
+ *      buffered), :804-862 (choice of the nthreads_m x nthreads_n grid), gemm_thread_mn.c:43-61 (divide_rule[]).
+ *      Panels travel by copy-engine pulls from the owners' windows (CUDA IPC over NVLink) announced with stream
+ *      memory operations -- no SM is taken from the local GEMM; B200_SUMMA_TRANSPORT=nccl switches to ncclBroadcast
+ *      on row / column communicators.  NCCL (dlopen'ed) bootstraps the group from the 128-byte id every rank gets
+ *      from rank 0 by whatever means the caller has (MPI_Bcast, torch.distributed, a file).  All calls return 0 or
+ *      non-zero with b200_last_error() set; create / gemm / destroy are collective. ----------------------------- */
+typedef struct b200_summa b200_summa;
+int      b200_summa_unique_id(void *id128);
+void     b200_summa_grid(int world, int *P, int *Q);                       /* 2 -> 1x2, 4 -> 2x2, 8 -> 2x4 (divide_rule[]) */
+int      b200_summa_create(b200_summa **handle, const void *id128, int rank, int world, int P, int Q);
+int      b200_summa_destroy(b200_summa *handle);
+int64_t  b200_summa_numroc(int64_t n, int64_t nb, int iproc, int nprocs);  /* local extent of a block-cyclic dimension */
+int64_t  b200_summa_schedule(int64_t k, int64_t nb, int P, int Q, int64_t capacity, int64_t *k0, int64_t *width, int *a_owner_col,
+                             int64_t *a_local_col, int *b_owner_row, int64_t *b_local_row);
+/* C := alpha A B + beta C, global m x n x k, block nb; this rank (p = rank / Q, q = rank % Q) passes its local pieces
+ * a_loc (numroc(m,nb,p,P) x numroc(k,nb,q,Q)), b_loc (numroc(k,nb,p,P) x numroc(n,nb,q,Q)), c_loc (numroc(m,nb,p,P) x
+ * numroc(n,nb,q,Q)), column-major, device or host memory; the local products run on `stream` (cudaStream_t). */
+int      b200_summa_gemm(b200_summa *handle, int dtype, int64_t m, int64_t n, int64_t k, int64_t nb, const void *alpha,
+                         const void *a_loc, int64_t lda, const void *b_loc, int64_t ldb, const void *beta, void *c_loc,
+                         int64_t ldc, void *stream);
+uint64_t b200_summa_launches(const b200_summa *handle);
+const char *b200_summa_describe(const b200_summa *handle);
+
 /* ---- error hook (driver/others/xerbla.c:56-73): weak, a caller's own xerbla_ wins ---- */
 int xerbla_(char *name, blasint *info, blasint len);
 

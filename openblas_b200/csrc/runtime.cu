@@ -737,6 +737,20 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
 
 #include "runtime_level3.inl"
 
+/* summa.cu: one local product of the distributed driver, column-major NN on device pointers, enqueued on `stream` */
+int summa_local_gemm(int dtype, int64_t m, int64_t n, int64_t k, const void *alpha, const void *a, int64_t lda, const void *b,
+                     int64_t ldb, const void *beta, void *c, int64_t ldc, cudaStream_t stream) {
+  if (m <= 0 || n <= 0) return 0;
+  b200_problem p = {dtype, B200_N, B200_N, m, n, k, lda, ldb, ldc, alpha, beta, a, b, c};
+  DeviceGemm g;
+  g.dtype = dtype; g.transa = B200_N; g.transb = B200_N; g.m = m; g.n = n; g.k = k;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a = a; g.b = b; g.c = c;
+  read_scalars(&p, g);
+  CK(dispatch(g, stream));
+  return 0;
+}
+void summa_set_error(const char *msg) { snprintf(t_error, sizeof t_error, "%s", msg); }
+
 }  // namespace b200
 
 /* ------------------------------------------------------------------------ C ABI ---- */

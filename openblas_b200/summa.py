@@ -214,3 +214,81 @@ def scatter_from_global(full, nb, grid, rows_by, cols_by):
     ri_t = torch.tensor(ri, dtype=torch.long, device=full.device)
     ci_t = torch.tensor(ci, dtype=torch.long, device=full.device)
     return full.index_select(0, ci_t).index_select(1, ri_t).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The driver inside the library (csrc/summa.cu) through its C symbols; the class above is its host-side mirror
+# (same grid, same distribution, same schedule -- tests/test_summa_cpu.py checks them against each other) and
+# the path that runs under gloo on CPU.
+class CSumma:
+    """b200_summa_* of libopenblas_b200.so: SUMMA over peer windows (CUDA IPC + copy engines + stream memory
+    operations), NCCL bootstrapped from an id this class distributes with torch.distributed."""
+
+    def __init__(self, world=None, rank=None, device=None):
+        import ctypes as C
+        from ._lib import lib
+        self.C, self.lib = C, lib()
+        L = self.lib
+        L.b200_summa_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.b200_summa_destroy.argtypes = [C.c_void_p]
+        L.b200_summa_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.b200_summa_launches.restype = C.c_uint64
+        L.b200_summa_launches.argtypes = [C.c_void_p]
+        L.b200_summa_describe.restype = C.c_char_p
+        L.b200_summa_describe.argtypes = [C.c_void_p]
+        L.b200_last_error.restype = C.c_char_p
+        self.world = dist.get_world_size() if world is None else world
+        self.rank = dist.get_rank() if rank is None else rank
+        self.P, self.Q = grid_shape(self.world)
+        self.p, self.q = self.rank // self.Q, self.rank % self.Q
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (C.c_char * 128)()
+                if L.b200_summa_unique_id(buf):
+                    raise RuntimeError(L.b200_last_error().decode())
+                ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            on_dev = ident.to(dev) if dist.get_backend() == "nccl" else ident
+            dist.broadcast(on_dev, src=0)
+            ident = on_dev.cpu()
+        raw = bytes(ident.numpy().tobytes())
+        self.handle = C.c_void_p()
+        if L.b200_summa_create(C.byref(self.handle), raw, self.rank, self.world, self.P, self.Q):
+            raise RuntimeError(L.b200_last_error().decode())
+
+    def local_shapes(self, m, n, k, nb):
+        """(m_loc, n_loc, ka_loc, kb_loc) of this rank"""
+        return (numroc(m, nb, self.p, self.P), numroc(n, nb, self.q, self.Q), numroc(k, nb, self.q, self.Q), numroc(k, nb, self.p, self.P))
+
+    def gemm(self, dtype_code, m, n, k, nb, alpha, a_loc, lda, b_loc, ldb, beta, c_loc, ldc, stream=None):
+        """a_loc / b_loc / c_loc: torch tensors (device, or pinned / pageable host) or raw addresses"""
+        from .cblas import addr, scalar_array
+        al, be = scalar_array(dtype_code, alpha), scalar_array(dtype_code, beta)
+        if self.lib.b200_summa_gemm(self.handle, dtype_code, m, n, k, nb, al.ctypes.data, addr(a_loc), lda, addr(b_loc), ldb, be.ctypes.data,
+                                    addr(c_loc), ldc, stream):
+            raise RuntimeError(self.lib.b200_last_error().decode())
+
+    def launches(self):
+        return int(self.lib.b200_summa_launches(self.handle))
+
+    def describe(self):
+        return self.lib.b200_summa_describe(self.handle).decode()
+
+    def close(self):
+        if self.handle:
+            self.lib.b200_summa_destroy(self.handle)
+            self.handle = None
+
+
+def hashed_entries(tag, gi, gj):
+    """Deterministic pseudo-random entries in [-0.5, 0.5) of the GLOBAL matrix `tag` at rows gi x columns gj (int64
+    torch tensors, any device): every rank can regenerate any row or column of A and B without communication, which
+    is what lets each rank check sampled entries of its C block against long-double dot products.  Returns a
+    (len(gj), len(gi)) float64 tensor (column-major storage of the piece)."""
+    x = (gi[None, :] * 2654435761 + gj[:, None] * 40503 + tag * 7919) & 0xFFFFFFFF
+    x = x ^ (x >> 16)
+    x = (x * 0x45D9F3B) & 0xFFFFFFFF
+    x = x ^ (x >> 16)
+    return x.to(torch.float64) * (1.0 / 4294967296.0) - 0.5

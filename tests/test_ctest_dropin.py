@@ -40,10 +40,13 @@ def test_ctest_level3_gemm(p):
 
 @pytest.mark.parametrize("p", list("cz"))
 def test_ctest_level3_gemm3m(p):
-    """ctest/Makefile:168-176,210-225: x?cblat3_3m < ?in3_3m -- the GEMM3M flavour of the complex drivers
-    (c_?blat3c_3m.c, c_?blas3_3m.c, c_?3chke_3m.c): cblas_?gemm3m computational sweeps in both layouts and its
-    error exits, judged by the reference's own checker."""
-    import re
+    """ctest/Makefile:168-176,210-225: x?cblat3_3m < ?in3_3m, the GEMM3M flavour of the complex drivers
+    (c_?blat3c_3m.c, c_?blas3_3m.c, c_?3chke_3m.c), linked against this library alone.  The f2c'd driver the reference
+    ships for builds without a Fortran compiler matches routine names in 12 characters and "cblas_?gemm3m" has 13, so
+    it reports every routine as NOT TESTED -- against the reference itself as well: the transcript of the same
+    binary linked against oracle/_ref/generic is committed (tests/golden/ctest_3m_reference_transcript_?.txt) and
+    ours must equal it line for line.  The sweep the Fortran driver would run (c_?blat3_3m.f, ?CHK1) is restated in
+    tests/test_gemm_gpu.py::test_gemm3m_over_the_ctest_grid."""
     exe = os.path.join(CTEST, f"x{p}cblat3_3m")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/ctest not built (needs /root/reference at build time)")
@@ -53,9 +56,8 @@ def test_ctest_level3_gemm3m(p):
     print(out[-3000:])
     assert r.returncode == 0, out[-2000:]
     assert "FATAL" not in out and "FAIL" not in out.replace("FAILURES", ""), out[-2000:]
-    assert len(re.findall(rf"cblas_{p}gemm3m\s+PASSED THE TESTS OF ERROR-EXITS", out)) == 1, out[-2000:]
-    assert re.search(rf"cblas_{p}gemm3m\s+PASSED THE COLUMN-MAJOR COMPUTATIONAL TESTS \(\s*\d+ CALLS\)", out), out[-2000:]
-    assert re.search(rf"cblas_{p}gemm3m\s+PASSED THE ROW-MAJOR\s+COMPUTATIONAL TESTS \(\s*\d+ CALLS\)", out), out[-2000:]
+    want = open(os.path.join(ROOT, "tests", "golden", f"ctest_3m_reference_transcript_{p}.txt")).read()
+    assert out.splitlines() == want.splitlines()
 
 
 def test_compare_sgemm_sbgemm():

@@ -199,6 +199,46 @@ def test_sbgemm_vs_sgemm_like_reference_test(ob, oracle):
                 assert np.max(np.abs(cc - dd)) <= SBGEMM_ABS_TOL
 
 
+@pytest.mark.parametrize("dtype", [cpu.CX, cpu.Z])
+def test_gemm3m_over_the_ctest_grid(ob, oracle, dtype):
+    """The sweep of the reference's GEMM3M acceptance driver (ctest/c_zblat3_3m.f ZCHK1 with ctest/zin3_3m: every
+    m, n, k in {0, 1, 2, 3, 5, 9, 35}, the nine N/T/C combinations, alpha and beta from the file's grids, both
+    layouts), through cblas_?gemm3m, judged like the driver does (ZMMCH: err / (eps * gauge) < 16) plus the
+    componentwise bound and untouched padding.  Row-major calls pass the transposed problem's storage."""
+    rng = np.random.default_rng(33 + dtype)
+    alphas, betas = alpha_beta(dtype)
+    fn = ob.cblas.cgemm3m if dtype == cpu.CX else ob.cblas.zgemm3m
+    sizes = (0, 1, 2, 3, 5, 9, 35)
+    calls = 0
+    for order in (ob.cblas.ColMajor, ob.cblas.RowMajor):
+        for m in sizes:
+            for n in sizes:
+                for k in (sizes if order == ob.cblas.ColMajor else (0, 3, 35)):
+                    for ta in (0, 1, 3):
+                        for tb in (0, 1, 3):
+                            ai, bi = rng.integers(0, 3), rng.integers(0, 3)
+                            alpha, beta = alphas[ai], betas[bi]
+                            if order == ob.cblas.ColMajor:
+                                a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k)
+                                got = c0.copy()
+                                fn(order, CB[ta], CB[tb], m, n, k, alpha, a, lda, b, ldb, beta, got, ldc)
+                                if m and n:
+                                    check(oracle, dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, got, "3m-col")
+                                else:
+                                    assert np.array_equal(got.view(np.uint8), c0.view(np.uint8))
+                            else:
+                                # row-major C (m x n) = column-major C^T (n x m) = op(B)^T op(A)^T: the column-major problem (tb, ta, n, m, k)
+                                b_, ldb, a_, lda, c0, ldc = problem(rng, oracle, dtype, tb, ta, n, m, k)
+                                got = c0.copy()
+                                fn(order, CB[ta], CB[tb], m, n, k, alpha, a_, lda, b_, ldb, beta, got, ldc)
+                                if m and n:
+                                    check(oracle, dtype, tb, ta, n, m, k, alpha, b_, ldb, a_, lda, beta, c0, ldc, got, "3m-row")
+                                else:
+                                    assert np.array_equal(got.view(np.uint8), c0.view(np.uint8))
+                            calls += 1
+    assert calls == 7 * 7 * 7 * 9 + 7 * 7 * 3 * 9
+
+
 def test_gemm3m_and_batch(ob, oracle):
     """f1/f2 of SURVEY 8(f): gemm3m has the GEMM contract; gemm_batch runs every matrix of every
     group (interface/gemm_batch.c:322-366)."""

@@ -102,3 +102,34 @@ def test_summa_gloo_matches_oracle(world, shape):
         err, launches, steps = out[rank]
         assert err < 1e-12, (rank, err)
         assert launches == steps == (k + nb - 1) // nb
+
+
+def test_c_driver_layout_functions_agree_with_the_python_mirror():
+    """b200_summa_numroc / b200_summa_schedule / b200_summa_grid (csrc/summa.cu; no CUDA call behind them) against
+    numroc / panel_schedule / GRID of openblas_b200/summa.py, which the gloo sweeps above exercise."""
+    import ctypes as C
+    import openblas_b200 as ob
+    from openblas_b200 import summa
+    L = ob.lib()
+    L.b200_summa_numroc.restype = C.c_int64
+    L.b200_summa_numroc.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int]
+    L.b200_summa_schedule.restype = C.c_int64
+    L.b200_summa_schedule.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 6
+    for n in (0, 1, 5, 100, 1000, 32768, 65537):
+        for nb in (1, 7, 64, 2048):
+            for P in (1, 2, 3, 4, 8):
+                got = [L.b200_summa_numroc(n, nb, i, P) for i in range(P)]
+                assert got == [summa.numroc(n, nb, i, P) for i in range(P)] and sum(got) == n
+                assert got == [len(summa.local_index_map(n, nb, i, P)) for i in range(P)]
+    for world, want in summa.GRID.items():
+        P, Q = C.c_int(), C.c_int()
+        L.b200_summa_grid(world, C.byref(P), C.byref(Q))
+        assert (P.value, Q.value) == want
+    for (k, nb, P, Q) in ((0, 4, 2, 2), (10, 4, 2, 4), (32768, 4096, 2, 4), (1000, 64, 3, 5), (7, 8, 1, 2)):
+        steps = summa.panel_schedule(k, nb, P, Q)
+        cap = len(steps) + 2
+        k0, w, al, bl = ((C.c_int64 * cap)() for _ in range(4))
+        ao, bo = (C.c_int * cap)(), (C.c_int * cap)()
+        cnt = L.b200_summa_schedule(k, nb, P, Q, cap, k0, w, ao, al, bo, bl)
+        assert cnt == len(steps)
+        assert [(k0[i], w[i], ao[i], al[i], bo[i], bl[i]) for i in range(cnt)] == steps
