@@ -717,6 +717,10 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
 
   /* large host operands: strided DMA straight from / to the caller's memory (full PCIe
    * rate when it is pinned; staged by the driver when it is pageable) */
+  static const bool trace = getenv("B200_TRACE") != nullptr;      /* B200_TRACE=1: per-phase host timestamps of this path on stderr */
+  const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  double t_up = 0, t_launch = 0, t_down = 0, t_drain = 0;
   for (int i = 0; i < 3; i++) {
     Operand &o = *ops[i];
     if (o.kind == PTR_DEVICE) continue;
@@ -725,13 +729,20 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
     if ((err = h2d_any(ctx, s, o.kind, o.dev, (size_t)o.ld_dev * o.es, o.host, (size_t)o.ld_user * o.es,
                        (size_t)o.rows * o.es, (size_t)o.cols))) return err;
   }
+  t_up = since();
   CK(dispatch(g, s));
+  t_launch = since();
   if (C.kind != PTR_DEVICE) {
     if ((err = d2h_any(ctx, s, C.kind, (char *)p->c, (size_t)C.ld_user * C.es, C.dev, (size_t)C.ld_dev * C.es,
                        (size_t)C.rows * C.es, (size_t)C.cols))) return err;
+    t_down = since();
     if ((err = drain_all_out(ctx))) return err;
+    t_drain = since();
   }
   CK(cudaStreamSynchronize(s));
+  if (trace)
+    fprintf(stderr, "b200 trace %lldx%lldx%lld: uploads enqueued %.3f ms, kernel enqueued %.3f, download enqueued %.3f, drained %.3f, done %.3f\n",
+            (long long)p->m, (long long)p->n, (long long)p->k, t_up, t_launch, t_down, t_drain, since());
   return 0;
 }
 

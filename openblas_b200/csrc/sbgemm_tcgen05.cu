@@ -586,31 +586,64 @@ cudaError_t launch_2cta_variant(const DeviceGemm &g, cudaStream_t stream) {
 
 }  // namespace
 
-cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t stream) {
+/* column-major bf16 block copy into a 16-byte aligned, pitch % 8 == 0 layout (operands TMA cannot address in place) */
+__global__ void __launch_bounds__(256) repack_bf16_kernel(int64_t rows, int64_t cols, const uint16_t *__restrict__ src, int64_t ld_src,
+                                                          uint16_t *__restrict__ dst, int64_t ld_dst) {
+  const int64_t tiles_r = (rows + 255) / 256;
+  for (int64_t t = blockIdx.x; t < tiles_r * cols; t += gridDim.x) {
+    const int64_t r = (t % tiles_r) * 256 + threadIdx.x, c = t / tiles_r;
+    if (r < rows) dst[r + c * ld_dst] = src[r + c * ld_src];
+  }
+}
+
+cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g_in, cudaStream_t stream) {
+  DeviceGemm g = g_in;
   if (g.dtype != B200_SB || g.tri) return cudaErrorNotSupported;
-  /* TMA: 16-byte aligned bases, row pitch a multiple of 16 bytes; int32 tile arithmetic */
-  if (((uintptr_t)g.a | (uintptr_t)g.b) & 15) return cudaErrorNotSupported;
-  if ((g.lda % 8) || (g.ldb % 8) || ((uintptr_t)g.c & 3)) return cudaErrorNotSupported;
-  if (g.m < BLOCK_M || g.n < BLOCK_N || g.k < BLOCK_K) return cudaErrorNotSupported;  /* boxes never exceed the tensor */
+  if ((uintptr_t)g.c & 3) return cudaErrorNotSupported;
+  if (g.m < 1 || g.n < 1 || g.k < 1) return cudaErrorNotSupported;
   if (g.m > (1 << 30) || g.n > (1 << 30) || g.k > (1 << 30)) return cudaErrorNotSupported;
   if (((g.m + BLOCK_M - 1) / BLOCK_M) * ((g.n + BLOCK_N - 1) / BLOCK_N) > (1ll << 30)) return cudaErrorNotSupported;
   const bool a_mn = !(g.transa & 1), b_mn = (g.transb & 1);
+  /* TMA needs 16-byte aligned bases and pitches that are multiples of 16 bytes.  An operand that is not (odd leading
+   * dimension, a sub-matrix starting at an odd column) is copied ONCE into an aligned stream-ordered temporary by an
+   * HBM-bound pass (2 bytes read + 2 written per element against 2 n or 2 m flops per element in the product) --
+   * the reference's AMX kernel (sbgemm_kernel_16x16_spr_tmpl.c) repacks EVERY operand; here only misaligned ones.
+   * Boxes may exceed the tensor (TMA zero-fills), so small and ragged extents need nothing special. */
+  void *tmp[2] = {nullptr, nullptr};
+  auto fix = [&](const void *&ptr, int64_t &ld, int64_t rows, int64_t cols, int which) -> cudaError_t {
+    if ((((uintptr_t)ptr) & 15) == 0 && ld % 8 == 0) return cudaSuccess;
+    const int64_t ld2 = (rows + 7) / 8 * 8;
+    cudaError_t e = cudaMallocAsync(&tmp[which], (size_t)ld2 * (size_t)cols * 2, stream);
+    if (e != cudaSuccess) return e;
+    int64_t blocks = ((rows + 255) / 256) * cols;
+    if (blocks > 8 * (int64_t)sm_count()) blocks = 8 * (int64_t)sm_count();
+    repack_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(rows, cols, (const uint16_t *)ptr, ld, (uint16_t *)tmp[which], ld2);
+    count_launch("repack_bf16");
+    ptr = tmp[which]; ld = ld2;
+    return cudaGetLastError();
+  };
+  cudaError_t e = fix(g.a, g.lda, a_mn ? g.m : g.k, a_mn ? g.k : g.m, 0);
+  if (e == cudaSuccess) e = fix(g.b, g.ldb, b_mn ? g.n : g.k, b_mn ? g.k : g.n, 1);
+  if (e != cudaSuccess) { for (void *t : tmp) if (t) cudaFreeAsync(t, stream); return e; }
   static int cfg = -1;
-  if (cfg < 0) { const char *ev = getenv("B200_SBGEMM_CFG"); cfg = ev ? atoi(ev) : 2; }   /* 2 = CTA pairs (default), 1 = single CTA */
-  cudaError_t e;
-  if (cfg == 2) {
+  if (cfg < 0) { const char *ev = getenv("B200_SBGEMM_CFG"); cfg = ev ? atoi(ev) : 0; }   /* 2 = CTA pairs, 1 = single CTA, 0 = by shape */
+  /* CTA pairs work on 256 x 256 tiles; with at most 128 rows half of every pair would multiply zeros: single CTAs
+   * (128 x 256 tiles) take those */
+  const int use = cfg ? cfg : (g.m <= 128 ? 1 : 2);
+  if (use == 2) {
     if (a_mn && b_mn) e = launch_2cta_variant<true, true>(g, stream);
     else if (a_mn && !b_mn) e = launch_2cta_variant<true, false>(g, stream);
     else if (!a_mn && b_mn) e = launch_2cta_variant<false, true>(g, stream);
     else e = launch_2cta_variant<false, false>(g, stream);
     if (e == cudaSuccess) count_launch("sbgemm_tcgen05_2cta_256x256x64");
-    return e;
+  } else {
+    if (a_mn && b_mn) e = launch_variant<true, true>(g, stream);
+    else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream);
+    else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream);
+    else e = launch_variant<false, false>(g, stream);
+    if (e == cudaSuccess) count_launch("sbgemm_tcgen05_128x256x64");
   }
-  if (a_mn && b_mn) e = launch_variant<true, true>(g, stream);
-  else if (a_mn && !b_mn) e = launch_variant<true, false>(g, stream);
-  else if (!a_mn && b_mn) e = launch_variant<false, true>(g, stream);
-  else e = launch_variant<false, false>(g, stream);
-  if (e == cudaSuccess) count_launch("sbgemm_tcgen05_128x256x64");
+  for (void *t : tmp) if (t) cudaFreeAsync(t, stream);
   return e;
 }
 

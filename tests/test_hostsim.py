@@ -352,13 +352,28 @@ def test_extension_api_and_kernel_forcing(sim, oracle):
         assert np.array_equal(got, want)
         for p in dev:
             sim.hostsim_free(p)
-        sim.b200_set_kernel(2)                       # FAST: an SBGEMM the tcgen05 kernel refuses (m < 128)
+        sim.b200_set_kernel(2)                       # FAST: a ZGEMM the DMMA kernel refuses (device operands only 8-byte aligned)
         assert sim.b200_get_kernel() == 2
+        za = (rng.random((k, m)) + 1j * rng.random((k, m))).astype(np.complex128)
+        zb = (rng.random((n, k)) + 1j * rng.random((n, k))).astype(np.complex128)
+        zc = np.zeros((n, m), dtype=np.complex128)
+        dev = []
+        for x in (za, zb, zc):
+            p = sim.hostsim_device_alloc(x.nbytes + 16)
+            C.memmove(p + 8, x.ctypes.data, x.nbytes)
+            dev.append(p)
+        za1, zb0 = np.array([1.0, 0.0]), np.array([0.0, 0.0])
+        rc = sim.b200_gemm(3, 0, 0, i64(m), i64(n), i64(k), P(za1), C.c_void_p(dev[0] + 8), i64(m), C.c_void_p(dev[1] + 8), i64(k), P(zb0),
+                           C.c_void_p(dev[2] + 8), i64(m))
+        assert rc == 801, rc
+        for p in dev:
+            sim.hostsim_free(p)
+        # an SBGEMM below the old tcgen05 minimums (m < 128) is taken by the fast path now
         ha, hb = oracle.tobf16(rng.random((k, m), dtype=np.float32)), oracle.tobf16(rng.random((n, k), dtype=np.float32))
         hc = np.zeros((n, m), dtype=np.float32)
         fa, fb = np.array([1.0], dtype=np.float32), np.array([0.0], dtype=np.float32)
         rc = sim.b200_gemm(4, 0, 0, i64(m), i64(n), i64(k), P(fa), P(ha), i64(m), P(hb), i64(k), P(fb), P(hc), i64(m))
-        assert rc == 801, rc
+        assert rc == 0 and sim.b200_last_kernel() == b"sim_sbgemm", (rc, sim.b200_last_kernel())
     finally:
         sim.b200_set_kernel(0)
 

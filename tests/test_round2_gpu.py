@@ -156,3 +156,29 @@ def test_shutdown_releases_and_the_next_call_initialises_again(ob, oracle):
         ob.cblas.dgemm(ob.cblas.ColMajor, CB[0], CB[0], m, n, k, 0.7, a, lda, b, ldb, 1.3, got, ldc)
         check(oracle, cpu.D, 0, 0, m, n, k, 0.7, a, lda, b, ldb, 1.3, c0, ldc, got, "around-shutdown")
         ob.lib().b200_shutdown()
+
+
+def test_sbgemm_small_ragged_and_misaligned_shapes_stay_on_tcgen05(ob, oracle):
+    """Round 1 sent SBGEMM to the CUDA-core generic kernel for m < 128, n < 256, k < 64, lda % 8 != 0 or a base that
+    is not 16-byte aligned (VERDICT missing #7).  TMA boxes may exceed the tensor (zero fill), and misaligned operands
+    are repacked once on the device, so every shape from 64^3 up runs on tcgen05.mma: all four op combinations,
+    ragged extents, odd leading dimensions, a sub-matrix view starting at an odd element, beta != 0 / beta == 0 over NaN."""
+    import torch
+    rng = np.random.default_rng(808)
+    for (m, n, k, pad, skew) in [(64, 64, 64, (0, 0, 0), 0), (100, 130, 70, (8, 8, 3), 0), (128, 255, 63, (1, 3, 5), 0), (129, 257, 65, (7, 5, 1), 0),
+                                 (300, 77, 513, (8, 16, 0), 1), (36, 500, 96, (3, 0, 2), 3), (513, 130, 17, (0, 0, 1), 0)]:
+        for ta in range(2):
+            for tb in range(2):
+                a, lda, b, ldb, c0, ldc = problem(rng, oracle, cpu.SB, ta, tb, m, n, k, pad=pad)
+                for alpha, beta in ((0.7, 1.3), (1.0, 0.0)):
+                    start = c0.copy()
+                    if beta == 0.0:
+                        start[:, :m] = np.nan
+                    # device copies with `skew` extra leading elements: the operand starts at a 2 * skew byte offset
+                    da = torch.zeros(a.size + skew, dtype=torch.int16, device="cuda"); da[skew:] = torch.from_numpy(a.view(np.int16).ravel()).cuda()
+                    db = torch.zeros(b.size + skew, dtype=torch.int16, device="cuda"); db[skew:] = torch.from_numpy(b.view(np.int16).ravel()).cuda()
+                    dc = torch.from_numpy(start.copy()).cuda()
+                    ob.cblas.gemm_any(cpu.SB, ta, tb, m, n, k, alpha, da.data_ptr() + 2 * skew, lda, db.data_ptr() + 2 * skew, ldb, beta, dc, ldc)
+                    kern = ob.cblas.last_kernel()
+                    assert "tcgen05" in kern, (kern, m, n, k, pad, skew)
+                    check(oracle, cpu.SB, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, dc.cpu().numpy(), kern)
