@@ -102,8 +102,9 @@ cudaError_t launch_sbdot(int64_t n, const void *x, int64_t incx, const void *y, 
                          cudaStream_t stream);
 
 /* level3_aux.cu: helpers of the symmetric level-3 family */
+/* the region rows [i0, i0 + nr) x columns [j0, j0 + nc) of the full matrix (nr / nc < 0: everything) */
 cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out,
-                                    int64_t ldo, cudaStream_t stream);
+                                    int64_t ldo, cudaStream_t stream, int64_t i0 = 0, int64_t nr = -1, int64_t j0 = 0, int64_t nc = -1);
 cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const void *t, int64_t ldt, double beta_re,
                              double beta_im, void *c, int64_t ldc, cudaStream_t stream);
 

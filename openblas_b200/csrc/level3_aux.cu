@@ -16,6 +16,8 @@
  *     a scratch tile; syrk_k.c's syrk_beta scales only the triangle); Hermitian flavour zeroes
  *     the diagonal's imaginary part (zherk_kernel.c, zherk_beta.c).  T == nullptr means "0".
  */
+#include <cstdlib>
+#include <cstring>
 #include "gemm_common.cuh"
 
 namespace b200 {
@@ -32,17 +34,19 @@ template <class T> __device__ __forceinline__ T real_only(T v) { return v; }
 template <> __device__ __forceinline__ float2 real_only(float2 v) { return make_float2(v.x, 0.f); }
 template <> __device__ __forceinline__ double2 real_only(double2 v) { return make_double2(v.x, 0.0); }
 
+/* out(i - i0, j - j0) = full(i, j) for the region rows [i0, i0 + nr) x columns [j0, j0 + nc) of the n x n matrix */
 template <class T>
-__global__ void __launch_bounds__(256) expand_symmetric_kernel(int uplo, int herm, int64_t n, const T *__restrict__ a,
-                                                               int64_t lda, T *__restrict__ out, int64_t ldo) {
-  const int64_t tiles_i = (n + 31) / 32, tiles_j = (n + 7) / 8;
+__global__ void __launch_bounds__(256) expand_symmetric_kernel(int uplo, int herm, const T *__restrict__ a, int64_t lda,
+                                                               T *__restrict__ out, int64_t ldo, int64_t i0, int64_t nr, int64_t j0, int64_t nc) {
+  const int64_t tiles_i = (nr + 31) / 32, tiles_j = (nc + 7) / 8;
   for (int64_t t = blockIdx.x; t < tiles_i * tiles_j; t += gridDim.x) {
-    const int64_t i = (t % tiles_i) * 32 + threadIdx.x, j = (t / tiles_i) * 8 + threadIdx.y;
-    if (i >= n || j >= n) continue;
+    const int64_t li = (t % tiles_i) * 32 + threadIdx.x, lj = (t / tiles_i) * 8 + threadIdx.y;
+    if (li >= nr || lj >= nc) continue;
+    const int64_t i = i0 + li, j = j0 + lj;
     const bool stored = uplo ? (i >= j) : (i <= j);       /* lower: on or below the diagonal */
     T v = stored ? a[i + j * lda] : a[j + i * lda];
     if (herm) v = (i == j) ? real_only(v) : (stored ? v : conj_of(v));
-    out[i + j * ldo] = v;
+    out[li + lj * ldo] = v;
   }
 }
 
@@ -204,6 +208,117 @@ __global__ void __launch_bounds__(TRI_RHS * TRI_LANES) tri_block_kernel(int nb, 
   }
 }
 
+/* Real types: one THREAD per right-hand side with its 64 entries in REGISTERS (round 1's kernel above kept them in
+ * shared memory and spent ~40 us per 64 x 64 block on a chain of 64 shuffle-reduced dot products: 128 serial
+ * launches were a quarter of a DTRSM).  The block E sits in shared memory and every thread reads the same element at
+ * the same time (a broadcast, conflict free).  A solve is column oriented -- x_k = b_k / e_kk, then the 63 - k
+ * updates b_i -= e_ik x_k are independent FMAs -- so nothing but the 64 pivots is a dependent chain; a product is row
+ * oriented in the order that lets it run in place.  Blocks smaller than 64 are padded with the identity.  Right-hand
+ * sides that are rows of B (right-side TRSM, cs == 1) are read and written coalesced straight from global memory;
+ * columns of B (rs == 1) go through a shared-memory tile. */
+constexpr int TRR_THREADS = 64;
+template <class T, bool SOLVE, bool LOWER>
+__global__ void __launch_bounds__(TRR_THREADS) tri_block_reg_kernel(int nb, int64_t nrhs, int unit, const T *__restrict__ f, int64_t fs_i,
+                                                                    int64_t fs_k, T alpha, T *__restrict__ b, int64_t rs, int64_t cs) {
+  constexpr int N = TRI_NB;
+  extern __shared__ __align__(16) unsigned char tri_smem[];
+  T *E = reinterpret_cast<T *>(tri_smem);          /* SOLVE: E[k][i] (columns contiguous); product: E[i][k] */
+  T *Xs = E + N * N;                               /* [rhs][N + 1] staging tile when the right-hand sides are columns */
+  const int t = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * TRR_THREADS, c = c0 + t;
+  for (int idx = t; idx < N * N; idx += TRR_THREADS) {
+    const int i = fs_i == 1 ? idx % N : idx / N, k = fs_i == 1 ? idx / N : idx % N;
+    T v = (T)0;
+    if (i == k) {
+      v = (unit || i >= nb) ? (T)1 : f[i * fs_i + k * fs_k];
+      if (SOLVE) v = (T)1 / v;
+    } else if (i < nb && k < nb && (LOWER ? (k < i) : (k > i))) {
+      v = f[i * fs_i + k * fs_k];
+    }
+    E[SOLVE ? k * N + i : i * N + k] = v;
+  }
+  T x[N];
+  if (cs == 1) {
+#pragma unroll
+    for (int r = 0; r < N; r++) x[r] = (r < nb && c < nrhs) ? b[r * rs + c] : (T)0;
+    __syncthreads();
+  } else {
+    for (int idx = t; idx < N * TRR_THREADS; idx += TRR_THREADS) {
+      const int r = idx % N, cc = idx / N;
+      Xs[cc * (N + 1) + r] = (r < nb && c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < N; r++) x[r] = Xs[t * (N + 1) + r];
+  }
+  if (SOLVE) {
+#pragma unroll
+    for (int r = 0; r < N; r++) x[r] *= alpha;
+#pragma unroll
+    for (int kk = 0; kk < N; kk++) {
+      const int k = LOWER ? kk : N - 1 - kk;
+      x[k] *= E[k * N + k];                         /* 1 / diagonal (1 for a unit diagonal and for the padding) */
+      const T xk = x[k];
+      if (LOWER) {
+#pragma unroll
+        for (int i = k + 1; i < N; i++) x[i] = fma(-E[k * N + i], xk, x[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < k; i++) x[i] = fma(-E[k * N + i], xk, x[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ii = 0; ii < N; ii++) {
+      const int i = LOWER ? N - 1 - ii : ii;        /* in place: row i only needs entries the earlier rows have not overwritten */
+      T acc0 = (T)0, acc1 = (T)0;
+      if (LOWER) {
+#pragma unroll
+        for (int k = 0; k <= i; k++) { if (k & 1) acc1 = fma(E[i * N + k], x[k], acc1); else acc0 = fma(E[i * N + k], x[k], acc0); }
+      } else {
+#pragma unroll
+        for (int k = i; k < N; k++) { if (k & 1) acc1 = fma(E[i * N + k], x[k], acc1); else acc0 = fma(E[i * N + k], x[k], acc0); }
+      }
+      x[i] = alpha * (acc0 + acc1);
+    }
+  }
+  if (cs == 1) {
+#pragma unroll
+    for (int r = 0; r < N; r++) if (r < nb && c < nrhs) b[r * rs + c] = x[r];
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; r++) Xs[t * (N + 1) + r] = x[r];
+    __syncthreads();
+    for (int idx = t; idx < N * TRR_THREADS; idx += TRR_THREADS) {
+      const int r = idx % N, cc = idx / N;
+      if (r < nb && c0 + cc < nrhs) b[r * rs + (c0 + cc) * cs] = Xs[cc * (N + 1) + r];
+    }
+  }
+}
+
+template <class T, bool SOLVE, bool LOWER>
+cudaError_t tri_block_reg_launch(int nb, int64_t nrhs, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b, int64_t rs,
+                                 int64_t cs, cudaStream_t s) {
+  static bool configured = false;
+  auto kern = tri_block_reg_kernel<T, SOLVE, LOWER>;
+  const size_t smem = ((size_t)TRI_NB * TRI_NB + (size_t)TRR_THREADS * (TRI_NB + 1)) * sizeof(T);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<(unsigned)((nrhs + TRR_THREADS - 1) / TRR_THREADS), TRR_THREADS, smem, s>>>(nb, nrhs, unit, (const T *)f, fs_i, fs_k, (T)ar, (T *)b, rs, cs);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t tri_block_reg(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
+                          int64_t rs, int64_t cs, cudaStream_t s) {
+  if (solve) return eff_lower ? tri_block_reg_launch<T, true, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
+                              : tri_block_reg_launch<T, true, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  return eff_lower ? tri_block_reg_launch<T, false, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
+                   : tri_block_reg_launch<T, false, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+}
+
 template <class T, class R, bool SOLVE>
 cudaError_t tri_block_t(int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i, int64_t fs_k, double ar,
                         double ai, void *b, int64_t rs, int64_t cs, cudaStream_t s) {
@@ -221,10 +336,10 @@ cudaError_t tri_block_t(int nb, int64_t nrhs, int eff_lower, int unit, int cj, c
 }
 
 template <class T>
-cudaError_t expand_t(int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out, int64_t ldo, cudaStream_t s) {
-  const int64_t tiles = ((n + 31) / 32) * ((n + 7) / 8);
+cudaError_t expand_t(int uplo, int herm, const void *a, int64_t lda, void *out, int64_t ldo, int64_t i0, int64_t nr, int64_t j0, int64_t nc, cudaStream_t s) {
+  const int64_t tiles = ((nr + 31) / 32) * ((nc + 7) / 8);
   const int64_t cap = (int64_t)sm_count() * 16;
-  expand_symmetric_kernel<T><<<(unsigned)(tiles < cap ? tiles : cap), dim3(32, 8), 0, s>>>(uplo, herm, n, (const T *)a, lda, (T *)out, ldo);
+  expand_symmetric_kernel<T><<<(unsigned)(tiles < cap ? tiles : cap), dim3(32, 8), 0, s>>>(uplo, herm, (const T *)a, lda, (T *)out, ldo, i0, nr, j0, nc);
   return cudaGetLastError();
 }
 template <class T, class R>
@@ -239,14 +354,16 @@ cudaError_t merge_t(int uplo, int herm, int64_t n, const void *t, int64_t ldt, d
 }  // namespace
 
 cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out,
-                                    int64_t ldo, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
+                                    int64_t ldo, cudaStream_t stream, int64_t i0, int64_t nr, int64_t j0, int64_t nc) {
+  if (nr < 0) { i0 = 0; nr = n; }
+  if (nc < 0) { j0 = 0; nc = n; }
+  if (nr <= 0 || nc <= 0) return cudaSuccess;
   cudaError_t e;
   switch (dtype) {
-    case B200_S: e = expand_t<float>(uplo, 0, n, a, lda, out, ldo, stream); break;
-    case B200_D: e = expand_t<double>(uplo, 0, n, a, lda, out, ldo, stream); break;
-    case B200_C: e = expand_t<float2>(uplo, herm, n, a, lda, out, ldo, stream); break;
-    case B200_Z: e = expand_t<double2>(uplo, herm, n, a, lda, out, ldo, stream); break;
+    case B200_S: e = expand_t<float>(uplo, 0, a, lda, out, ldo, i0, nr, j0, nc, stream); break;
+    case B200_D: e = expand_t<double>(uplo, 0, a, lda, out, ldo, i0, nr, j0, nc, stream); break;
+    case B200_C: e = expand_t<float2>(uplo, herm, a, lda, out, ldo, i0, nr, j0, nc, stream); break;
+    case B200_Z: e = expand_t<double2>(uplo, herm, a, lda, out, ldo, i0, nr, j0, nc, stream); break;
     default: return cudaErrorNotSupported;
   }
   if (e == cudaSuccess) count_launch("expand_symmetric");
@@ -260,9 +377,11 @@ cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff
   cudaError_t e;
 #define TRI_CASE(T, R) (solve ? tri_block_t<T, R, true>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream) \
                               : tri_block_t<T, R, false>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream))
+  static const bool old_kernel = getenv("B200_TRI_KERNEL") && !strcmp(getenv("B200_TRI_KERNEL"), "smem");   /* round 1's kernel, for comparison */
+  const bool reg_ok = !old_kernel && (rs == 1 || cs == 1);
   switch (dtype) {
-    case B200_S: e = TRI_CASE(float, float); break;
-    case B200_D: e = TRI_CASE(double, double); break;
+    case B200_S: e = reg_ok ? tri_block_reg<float>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(float, float); break;
+    case B200_D: e = reg_ok ? tri_block_reg<double>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(double, double); break;
     case B200_C: e = TRI_CASE(float2, float); break;
     case B200_Z: e = TRI_CASE(double2, double); break;
     default: return cudaErrorNotSupported;

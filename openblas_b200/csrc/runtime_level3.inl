@@ -36,6 +36,34 @@ static cudaError_t gemm_on_device(int dtype, int ta, int tb, int64_t m, int64_t 
 
 static int64_t rankk_block(int64_t n) { return n >= 4096 ? 512 : n >= 1024 ? 256 : 128; }
 
+/* SYMM / HEMM: how many columns (side left) or rows (side right) of the symmetric operand are expanded at a time.
+ * The whole ka x ka matrix when that fits B200_SYMM_FULL_BYTES (one GEMM); otherwise panels of about
+ * B200_SYMM_PANEL_BYTES, i.e. ka / width GEMMs with inner dimension `width` accumulating into C -- a 65536^2 ZHEMM
+ * then needs 0.5 GiB of workspace instead of 64 GiB (round 1 expanded in full, always). */
+#ifdef B200_HOSTSIM
+#define B200_SYMM_FULL_BYTES  ((size_t)16 << 10)
+#define B200_SYMM_PANEL_BYTES ((size_t)8 << 10)
+#define B200_SYMM_PANEL_ALIGN 8
+#else
+#define B200_SYMM_FULL_BYTES  ((size_t)1 << 30)
+#define B200_SYMM_PANEL_BYTES ((size_t)512 << 20)
+#define B200_SYMM_PANEL_ALIGN 256
+#endif
+static int64_t symm_panel_width(int64_t ka, size_t es) {
+  /* B200_SYMM_FULL_MB / B200_SYMM_PANEL_MB override the limits (tests force the panel scheme at small sizes) */
+  static const size_t full_bytes = getenv("B200_SYMM_FULL_MB") ? (size_t)atol(getenv("B200_SYMM_FULL_MB")) << 20 : B200_SYMM_FULL_BYTES;
+  static const size_t panel_bytes = getenv("B200_SYMM_PANEL_MB") ? (size_t)atol(getenv("B200_SYMM_PANEL_MB")) << 20 : B200_SYMM_PANEL_BYTES;
+  if (round_up((size_t)ka * es, 128) * (size_t)ka <= full_bytes) return ka;
+  int64_t w = (int64_t)(panel_bytes / (round_up((size_t)ka * es, 128))) / B200_SYMM_PANEL_ALIGN * B200_SYMM_PANEL_ALIGN;
+  if (w < B200_SYMM_PANEL_ALIGN) w = B200_SYMM_PANEL_ALIGN;
+  return w < ka ? w : ka;
+}
+static size_t symm_scratch_bytes(int64_t ka, size_t es) {
+  const int64_t w = symm_panel_width(ka, es);
+  const size_t left = round_up((size_t)ka * es, 128) * (size_t)w, right = round_up((size_t)w * es, 128) * (size_t)ka;
+  return round_up(left > right ? left : right, 256);
+}
+
 /* ---- TRMM / TRSM: recursive splitting of the triangular matrix E = op(A) ------------------------
  * (the reference blocks the same routines over its GEMM kernel: driver/level3/trmm_L.c, trmm_R.c,
  * trsm_L.c, trsm_R.c).  E is cut at a multiple of 64 near the middle; the off-diagonal block is ONE
@@ -107,10 +135,28 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
       return 0;
     }
     const int64_t ka = p->side ? p->n : p->m;
-    const int64_t ldf = (int64_t)(round_up((size_t)ka * es, 128) / es);
-    CK(launch_expand_symmetric(p->dtype, p->uplo, p->routine == B200_HEMM, ka, a, lda, scratch, ldf, s));
-    if (!p->side) CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->m, ar, ai, scratch, ldf, b, ldb, br, bi, c, ldc, s));
-    else CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->n, ar, ai, b, ldb, scratch, ldf, br, bi, c, ldc, s));
+    const int64_t w = symm_panel_width(ka, es);
+    if (w >= ka) {                     /* the whole operand at once: ONE GEMM */
+      const int64_t ldf = (int64_t)(round_up((size_t)ka * es, 128) / es);
+      CK(launch_expand_symmetric(p->dtype, p->uplo, p->routine == B200_HEMM, ka, a, lda, scratch, ldf, s));
+      if (!p->side) CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->m, ar, ai, scratch, ldf, b, ldb, br, bi, c, ldc, s));
+      else CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, p->n, ar, ai, b, ldb, scratch, ldf, br, bi, c, ldc, s));
+      return 0;
+    }
+    /* panel by panel along the inner dimension: C := alpha A(:, K) B(K, :) + beta' C  /  alpha B(:, K) A(K, :) + beta' C */
+    for (int64_t k0 = 0; k0 < ka; k0 += w) {
+      const int64_t kw = ka - k0 < w ? ka - k0 : w;
+      const double pbr = k0 ? 1.0 : br, pbi = k0 ? 0.0 : bi;
+      if (!p->side) {
+        const int64_t ldf = (int64_t)(round_up((size_t)ka * es, 128) / es);
+        CK(launch_expand_symmetric(p->dtype, p->uplo, p->routine == B200_HEMM, ka, a, lda, scratch, ldf, s, 0, ka, k0, kw));
+        CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, kw, ar, ai, scratch, ldf, b + (size_t)k0 * es, ldb, pbr, pbi, c, ldc, s));
+      } else {
+        const int64_t ldw = (int64_t)(round_up((size_t)kw * es, 128) / es);
+        CK(launch_expand_symmetric(p->dtype, p->uplo, p->routine == B200_HEMM, ka, a, lda, scratch, ldw, s, k0, kw, 0, ka));
+        CK(gemm_on_device(p->dtype, 0, 0, p->m, p->n, kw, ar, ai, b + (size_t)k0 * (size_t)ldb * es, ldb, scratch, ldw, pbr, pbi, c, ldc, s));
+      }
+    }
     return 0;
   }
 
@@ -233,8 +279,8 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   }
   size_t scratch_bytes = 0;
   if (product && !trxm) {
-    const int64_t edge = symm ? A.rows : rankk_block(p->n);
-    scratch_bytes = round_up(round_up((size_t)edge * es, 128) * (size_t)edge, 256);
+    const int64_t edge = rankk_block(p->n);
+    scratch_bytes = symm ? symm_scratch_bytes(A.rows, es) : round_up(round_up((size_t)edge * es, 128) * (size_t)edge, 256);
   }
   int err = reserve_device(ctx, need + scratch_bytes);
   if (err) return err;

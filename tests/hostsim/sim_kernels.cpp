@@ -60,13 +60,13 @@ template <class R> std::complex<R> conj_if(std::complex<R> v, bool on) { return 
 template <class T> T real_part_only(T v) { return v; }
 template <class R> std::complex<R> real_part_only(std::complex<R> v) { return std::complex<R>(v.real(), 0); }
 
-template <class T> void expand(int uplo, int herm, int64_t n, const T *a, int64_t lda, T *out, int64_t ldo) {
-  for (int64_t j = 0; j < n; j++)
-    for (int64_t i = 0; i < n; i++) {
+template <class T> void expand(int uplo, int herm, const T *a, int64_t lda, T *out, int64_t ldo, int64_t i0, int64_t nr, int64_t j0, int64_t nc) {
+  for (int64_t j = j0; j < j0 + nc; j++)
+    for (int64_t i = i0; i < i0 + nr; i++) {
       const bool stored = uplo ? (i >= j) : (i <= j);
       T v = stored ? a[i + j * lda] : a[j + i * lda];
       if (herm) v = (i == j) ? real_part_only(v) : conj_if(v, !stored);
-      out[i + j * ldo] = v;
+      out[(i - i0) + (j - j0) * ldo] = v;
     }
 }
 template <class T> void merge(int uplo, int herm, int64_t n, const T *t, int64_t ldt, T beta, T *c, int64_t ldc) {
@@ -166,13 +166,16 @@ cudaError_t launch_convert(int dir, int64_t n, const void *in, int64_t inc_in, v
   return cudaSuccess;
 }
 
-cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out, int64_t ldo, cudaStream_t) {
-  if (n <= 0) return cudaSuccess;
+cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out, int64_t ldo, cudaStream_t,
+                                    int64_t i0, int64_t nr, int64_t j0, int64_t nc) {
+  if (nr < 0) { i0 = 0; nr = n; }
+  if (nc < 0) { j0 = 0; nc = n; }
+  if (nr <= 0 || nc <= 0) return cudaSuccess;
   switch (dtype) {
-    case B200_S: expand<float>(uplo, 0, n, (const float *)a, lda, (float *)out, ldo); break;
-    case B200_D: expand<double>(uplo, 0, n, (const double *)a, lda, (double *)out, ldo); break;
-    case B200_C: expand<std::complex<float>>(uplo, herm, n, (const std::complex<float> *)a, lda, (std::complex<float> *)out, ldo); break;
-    case B200_Z: expand<std::complex<double>>(uplo, herm, n, (const std::complex<double> *)a, lda, (std::complex<double> *)out, ldo); break;
+    case B200_S: expand<float>(uplo, 0, (const float *)a, lda, (float *)out, ldo, i0, nr, j0, nc); break;
+    case B200_D: expand<double>(uplo, 0, (const double *)a, lda, (double *)out, ldo, i0, nr, j0, nc); break;
+    case B200_C: expand<std::complex<float>>(uplo, herm, (const std::complex<float> *)a, lda, (std::complex<float> *)out, ldo, i0, nr, j0, nc); break;
+    case B200_Z: expand<std::complex<double>>(uplo, herm, (const std::complex<double> *)a, lda, (std::complex<double> *)out, ldo, i0, nr, j0, nc); break;
     default: return cudaErrorNotSupported;
   }
   count_launch("sim_expand_symmetric");

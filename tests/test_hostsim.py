@@ -176,8 +176,11 @@ def test_rank_k_schemes_and_symm_at_block_crossing_sizes(sim, oracle, dtype, ran
                 a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
                 alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
                 case = (0, dtype, herm, x, uplo, 0, m, n, 0, ka + 1, m + 2, m + 3, alpha, beta)
+                before = sim.b200_launch_count()
                 got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
                 L.check_case(case, got, want, gauge, K, touched, c0)
+                # the symmetric operand is bigger than the (host-simulation) full-expansion limit: expanded and multiplied panel by panel
+                assert sim.b200_launch_count() - before >= 6, sim.b200_launch_count() - before
                 for trans in (0, 1):
                     for (nn, k, beta_zero) in [(300, 24, False), (140, 33, True)]:
                         rows, cols = (k, nn) if trans else (nn, k)

@@ -200,3 +200,43 @@ def test_trsm_device_pointers_large(ob):
     X = b.T
     res = (A @ X - 0.7 * b0.T).abs().max().item()
     assert res < 1e-12, res
+
+
+def test_symm_hemm_panel_scheme_on_the_gpu(tmp_path):
+    """SYMM / HEMM with the full-expansion limit forced to zero (B200_SYMM_FULL_MB=0, read once per process, hence the
+    child process): the symmetric operand is expanded and multiplied in 256-wide panels along the inner dimension,
+    both sides, both triangles, NaN in the triangle that must not be read; against the oracle."""
+    import subprocess, sys, textwrap
+    script = tmp_path / "symm_panels.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+        import numpy as np
+        import openblas_b200 as ob
+        from oracle import cpu
+        import level3_helpers as L
+        oracle = cpu.Oracle()
+        call = L.bind(ob.lib())
+        rng = np.random.default_rng(4)
+        n_exp = 0
+        for dtype, herm in ((cpu.D, 0), (cpu.Z, 1), (cpu.CX, 0)):
+            cplx = dtype in (cpu.CX, cpu.Z)
+            for x in (0, 1):
+                for uplo in (0, 1):
+                    m, n = 600, 520
+                    ka = n if x else m
+                    a, b, c0 = L.operand(rng, dtype, ka, ka + 1), L.operand(rng, dtype, n, m + 2), L.operand(rng, dtype, n, m + 3)
+                    jj, ii = np.meshgrid(np.arange(ka), np.arange(ka + 1), indexing="ij")
+                    a[(ii < jj) if uplo else ((ii > jj) & (ii < ka))] = np.nan
+                    alpha, beta = ((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3))
+                    case = (0, dtype, herm, x, uplo, 0, m, n, 0, ka + 1, m + 2, m + 3, alpha, beta)
+                    before = ob.cblas.launch_count()
+                    got, want, gauge, K, touched = L.run_case(call, oracle, case, a, b, c0)
+                    L.check_case(case, got, want, gauge, K, touched, c0)
+                    assert ob.cblas.launch_count() - before == 2 * ((ka + 255) // 256), (ob.cblas.launch_count() - before, ka)
+                    n_exp += 1
+        print("PANELS OK", n_exp)
+    """))
+    env = dict(os.environ, B200_SYMM_FULL_MB="0", B200_SYMM_PANEL_MB="1")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PANELS OK 12" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
