@@ -109,7 +109,8 @@ cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const voi
                              double beta_im, void *c, int64_t ldc, cudaStream_t stream);
 
 cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cudaStream_t stream);
-/* base case of the recursive TRMM / TRSM: one nb x nb (nb <= 64) triangular block against nrhs vectors */
+/* base case of the recursive TRMM / TRSM: one nb x nb (nb <= tri_block_max(dtype)) triangular block against nrhs vectors */
+int tri_block_max(int dtype);
 cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,
                              int64_t fs_k, double ar, double ai, void *b, int64_t rs, int64_t cs, cudaStream_t stream);
 

@@ -208,115 +208,181 @@ __global__ void __launch_bounds__(TRI_RHS * TRI_LANES) tri_block_kernel(int nb, 
   }
 }
 
-/* Real types: one THREAD per right-hand side with its 64 entries in REGISTERS (round 1's kernel above kept them in
- * shared memory and spent ~40 us per 64 x 64 block on a chain of 64 shuffle-reduced dot products: 128 serial
- * launches were a quarter of a DTRSM).  The block E sits in shared memory and every thread reads the same element at
- * the same time (a broadcast, conflict free).  A solve is column oriented -- x_k = b_k / e_kk, then the 63 - k
- * updates b_i -= e_ik x_k are independent FMAs -- so nothing but the 64 pivots is a dependent chain; a product is row
- * oriented in the order that lets it run in place.  Blocks smaller than 64 are padded with the identity.  Right-hand
- * sides that are rows of B (right-side TRSM, cs == 1) are read and written coalesced straight from global memory;
- * columns of B (rs == 1) go through a shared-memory tile. */
-constexpr int TRR_THREADS = 64;
-template <class T, bool SOLVE, bool LOWER>
-__global__ void __launch_bounds__(TRR_THREADS) tri_block_reg_kernel(int nb, int64_t nrhs, int unit, const T *__restrict__ f, int64_t fs_i,
+/* Real types: the right-hand sides live in REGISTERS.  Round 1's kernel above keeps them in shared memory and spends
+ * ~40 us per 64 x 64 block on a chain of 64 shuffle-reduced dot products (128 serial launches: a quarter of a DTRSM).
+ * Here a GROUP of four adjacent lanes owns one right-hand side, 16 of its 64 entries each (row pairs 8q + 2h, 8q + 2h + 1
+ * for lane h of the group), and the algorithm is column oriented: for pivot k the owner finishes x_k (times the
+ * inverted diagonal), one shuffle hands it to the partner, and both apply the updates b_i -= e_ik x_k to their rows
+ * below -- independent FMAs fed by LDS.128 loads of column k of E that every pair reads at the same addresses
+ * (broadcast, conflict free) and that are all issued before the first FMA (32 registers of x leave room; a first
+ * version with 64 entries per thread had none left and serialised on every load: slower than round 1).  Only the
+ * 64 pivots form a dependent chain.  TRMM accumulates y = E x the same way into a second register set.  Blocks
+ * smaller than 64 are padded with the identity.  Right-hand sides that are rows of B (right side, cs == 1) are read
+ * and written straight from global memory, columns of B (rs == 1) through a shared-memory tile. */
+/* two instantiations: 64 x 64 blocks with 4 lanes x 16 rows per right-hand side (16 right-hand sides per 64-thread
+ * CTA), and 128 x 128 blocks with 8 lanes x 16 rows (32 per 256-thread CTA): the larger base case removes the deepest
+ * level of the recursion -- 64 GEMMs with k = 64 that ran at 1.4 TFLOP/s (47 us each, profiles/r02_dtrsm8192_launches_*) */
+template <class T> struct Pair2 { T x, y; };
+template <> struct __align__(16) Pair2<double> { double x, y; };
+template <> struct __align__(8) Pair2<float> { float x, y; };
+
+template <class T, int N, int LP, int TRR_RHS, bool SOLVE, bool LOWER>
+__global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int64_t nrhs, int unit, const T *__restrict__ f, int64_t fs_i,
                                                                     int64_t fs_k, T alpha, T *__restrict__ b, int64_t rs, int64_t cs) {
-  constexpr int N = TRI_NB;
+  constexpr int TRR_THREADS = LP * TRR_RHS, CH = 2 * LP, NQ = N / CH, NL = N / LP;   /* chunk of rows, chunks, rows per lane */
   extern __shared__ __align__(16) unsigned char tri_smem[];
-  T *E = reinterpret_cast<T *>(tri_smem);          /* SOLVE: E[k][i] (columns contiguous); product: E[i][k] */
-  T *Xs = E + N * N;                               /* [rhs][N + 1] staging tile when the right-hand sides are columns */
-  const int t = threadIdx.x;
-  const int64_t c0 = (int64_t)blockIdx.x * TRR_THREADS, c = c0 + t;
-  for (int idx = t; idx < N * N; idx += TRR_THREADS) {
-    const int i = fs_i == 1 ? idx % N : idx / N, k = fs_i == 1 ? idx / N : idx % N;
-    T v = (T)0;
-    if (i == k) {
-      v = (unit || i >= nb) ? (T)1 : f[i * fs_i + k * fs_k];
-      if (SOLVE) v = (T)1 / v;
-    } else if (i < nb && k < nb && (LOWER ? (k < i) : (k > i))) {
-      v = f[i * fs_i + k * fs_k];
+  T *E = reinterpret_cast<T *>(tri_smem);          /* E[k][i]: column k contiguous; SOLVE keeps 1 / e_kk on the diagonal */
+  T *Xs = E + N * N;                               /* [rhs][N + 1] staging tile when the right-hand sides are columns of B */
+  const int t = threadIdx.x, h = t % LP, rl = t / LP;
+  const int64_t c0 = (int64_t)blockIdx.x * TRR_RHS, c = c0 + rl;
+  /* the block: N * N / TRR_THREADS elements per thread, fetched in batches of 16 independent loads (one load per
+   * loop trip would pay the global-memory latency 64 times over: that, not the arithmetic, was most of the kernel) */
+  {
+    constexpr int BATCH = 16;
+    const bool col_major = fs_i == 1;               /* consecutive threads walk the contiguous direction of F */
+#pragma unroll 1
+    for (int base = 0; base < N * N; base += BATCH * TRR_THREADS) {
+      T v[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; j++) {
+        const int idx = base + j * TRR_THREADS + t;
+        const int i = col_major ? idx % N : idx / N, k = col_major ? idx / N : idx % N;
+        const bool diag = i == k, inside = i < nb && k < nb && (LOWER ? (k < i) : (k > i));
+        v[j] = ((diag && !unit && i < nb) || inside) ? f[i * fs_i + k * fs_k] : (diag ? (T)1 : (T)0);
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; j++) {
+        const int idx = base + j * TRR_THREADS + t;
+        const int i = col_major ? idx % N : idx / N, k = col_major ? idx / N : idx % N;
+        E[k * N + i] = (SOLVE && i == k) ? (T)1 / v[j] : v[j];
+      }
     }
-    E[SOLVE ? k * N + i : i * N + k] = v;
   }
-  T x[N];
+  /* my rows: CH q + 2 h + e, kept at x[2 q + e] */
+  T x[NL], y[SOLVE ? 1 : NL];
   if (cs == 1) {
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] = (r < nb && c < nrhs) ? b[r * rs + c] : (T)0;
+    for (int l = 0; l < NL; l++) {
+      const int r = CH * (l >> 1) + 2 * h + (l & 1);
+      x[l] = (r < nb && c < nrhs) ? b[r * rs + c] : (T)0;
+    }
     __syncthreads();
   } else {
-    for (int idx = t; idx < N * TRR_THREADS; idx += TRR_THREADS) {
-      const int r = idx % N, cc = idx / N;
-      Xs[cc * (N + 1) + r] = (r < nb && c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : (T)0;
+    {
+      constexpr int PER = N * TRR_RHS / TRR_THREADS;        /* 16 independent loads per thread, then the stores */
+      T v[PER];
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const int idx = j * TRR_THREADS + t, r = idx % N, cc = idx / N;
+        v[j] = (r < nb && c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : (T)0;
+      }
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const int idx = j * TRR_THREADS + t, r = idx % N, cc = idx / N;
+        Xs[cc * (N + 1) + r] = v[j];
+      }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] = Xs[t * (N + 1) + r];
+    for (int l = 0; l < NL; l++) x[l] = Xs[rl * (N + 1) + CH * (l >> 1) + 2 * h + (l & 1)];
   }
   if (SOLVE) {
 #pragma unroll
-    for (int r = 0; r < N; r++) x[r] *= alpha;
-#pragma unroll
-    for (int kk = 0; kk < N; kk++) {
-      const int k = LOWER ? kk : N - 1 - kk;
-      x[k] *= E[k * N + k];                         /* 1 / diagonal (1 for a unit diagonal and for the padding) */
-      const T xk = x[k];
-      if (LOWER) {
-#pragma unroll
-        for (int i = k + 1; i < N; i++) x[i] = fma(-E[k * N + i], xk, x[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < k; i++) x[i] = fma(-E[k * N + i], xk, x[i]);
-      }
-    }
+    for (int l = 0; l < NL; l++) x[l] *= alpha;
   } else {
 #pragma unroll
-    for (int ii = 0; ii < N; ii++) {
-      const int i = LOWER ? N - 1 - ii : ii;        /* in place: row i only needs entries the earlier rows have not overwritten */
-      T acc0 = (T)0, acc1 = (T)0;
-      if (LOWER) {
+    for (int l = 0; l < NL; l++) y[l] = (T)0;
+  }
+  const T *Eh = E + 2 * h;
+  const unsigned group_base = (unsigned)(t & 31) & ~(unsigned)(LP - 1);
+  /* column k of E for my rows of the chunks that still take part; the loads of column k + 1 are issued before the
+   * updates of column k (ptxas keeps only a few of them in flight; with 8 per column that is enough) */
+  Pair2<T> ecur[NQ], enext[NQ];
+  T dcur = (T)1, dnext = (T)1;
+  auto load_column = [&](Pair2<T> (&e)[NQ], T &d, int k) {
+    const int kq = k / CH;
 #pragma unroll
-        for (int k = 0; k <= i; k++) { if (k & 1) acc1 = fma(E[i * N + k], x[k], acc1); else acc0 = fma(E[i * N + k], x[k], acc0); }
+    for (int q = 0; q < NQ; q++)
+      if (LOWER ? (q >= kq) : (q <= kq)) e[q] = *reinterpret_cast<const Pair2<T> *>(Eh + k * N + CH * q);
+    if (SOLVE) d = E[k * N + k];                    /* 1 / diagonal (1 for a unit diagonal and for the padding) */
+  };
+  load_column(ecur, dcur, LOWER ? 0 : N - 1);
+#pragma unroll
+  for (int kk = 0; kk < N; kk++) {
+    const int k = LOWER ? kk : N - 1 - kk;
+    const int kq = k / CH, kh = (k % CH) >> 1, kl = 2 * kq + (k & 1);      /* chunk, owner lane of the group, owner's slot of row k */
+    if (kk + 1 < N) load_column(enext, dnext, LOWER ? k + 1 : k - 1);
+    T xk = x[kl];
+    if (SOLVE) xk *= dcur;
+    xk = __shfl_sync(0xffffffffu, xk, group_base | (unsigned)kh);
+    if (SOLVE && h == kh) x[kl] = xk;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      if (!(LOWER ? (q >= kq) : (q <= kq))) continue;
+      const int r0 = CH * q + 2 * h;                /* my two rows of this chunk */
+      if (SOLVE) {
+        /* rows strictly beyond the pivot; only the pivot's own chunk needs the test */
+        const bool on0 = q != kq || (LOWER ? r0 > k : r0 < k), on1 = q != kq || (LOWER ? r0 + 1 > k : r0 + 1 < k);
+        if (on0) x[2 * q] = fma(-ecur[q].x, xk, x[2 * q]);
+        if (on1) x[2 * q + 1] = fma(-ecur[q].y, xk, x[2 * q + 1]);
       } else {
-#pragma unroll
-        for (int k = i; k < N; k++) { if (k & 1) acc1 = fma(E[i * N + k], x[k], acc1); else acc0 = fma(E[i * N + k], x[k], acc0); }
+        const bool on0 = q != kq || (LOWER ? r0 >= k : r0 <= k), on1 = q != kq || (LOWER ? r0 + 1 >= k : r0 + 1 <= k);
+        if (on0) y[2 * q] = fma(ecur[q].x, xk, y[2 * q]);
+        if (on1) y[2 * q + 1] = fma(ecur[q].y, xk, y[2 * q + 1]);
       }
-      x[i] = alpha * (acc0 + acc1);
     }
+#pragma unroll
+    for (int q = 0; q < NQ; q++) ecur[q] = enext[q];
+    dcur = dnext;
+  }
+  if (!SOLVE) {
+#pragma unroll
+    for (int l = 0; l < NL; l++) x[l] = alpha * y[l];
   }
   if (cs == 1) {
 #pragma unroll
-    for (int r = 0; r < N; r++) if (r < nb && c < nrhs) b[r * rs + c] = x[r];
+    for (int l = 0; l < NL; l++) {
+      const int r = CH * (l >> 1) + 2 * h + (l & 1);
+      if (r < nb && c < nrhs) b[r * rs + c] = x[l];
+    }
   } else {
 #pragma unroll
-    for (int r = 0; r < N; r++) Xs[t * (N + 1) + r] = x[r];
+    for (int l = 0; l < NL; l++) Xs[rl * (N + 1) + CH * (l >> 1) + 2 * h + (l & 1)] = x[l];
     __syncthreads();
-    for (int idx = t; idx < N * TRR_THREADS; idx += TRR_THREADS) {
+    for (int idx = t; idx < N * TRR_RHS; idx += TRR_THREADS) {
       const int r = idx % N, cc = idx / N;
       if (r < nb && c0 + cc < nrhs) b[r * rs + (c0 + cc) * cs] = Xs[cc * (N + 1) + r];
     }
   }
 }
 
-template <class T, bool SOLVE, bool LOWER>
+template <class T, int N, int LP, int RHS, bool SOLVE, bool LOWER>
 cudaError_t tri_block_reg_launch(int nb, int64_t nrhs, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b, int64_t rs,
                                  int64_t cs, cudaStream_t s) {
   static bool configured = false;
-  auto kern = tri_block_reg_kernel<T, SOLVE, LOWER>;
-  const size_t smem = ((size_t)TRI_NB * TRI_NB + (size_t)TRR_THREADS * (TRI_NB + 1)) * sizeof(T);
+  auto kern = tri_block_reg_kernel<T, N, LP, RHS, SOLVE, LOWER>;
+  const size_t smem = ((size_t)N * N + (size_t)RHS * (N + 1)) * sizeof(T);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<(unsigned)((nrhs + TRR_THREADS - 1) / TRR_THREADS), TRR_THREADS, smem, s>>>(nb, nrhs, unit, (const T *)f, fs_i, fs_k, (T)ar, (T *)b, rs, cs);
+  kern<<<(unsigned)((nrhs + RHS - 1) / RHS), LP * RHS, smem, s>>>(nb, nrhs, unit, (const T *)f, fs_i, fs_k, (T)ar, (T *)b, rs, cs);
   return cudaGetLastError();
+}
+template <class T, int N, int LP, int RHS>
+cudaError_t tri_block_reg_n(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
+                            int64_t rs, int64_t cs, cudaStream_t s) {
+  if (solve) return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, true, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
+                              : tri_block_reg_launch<T, N, LP, RHS, true, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, false, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
+                   : tri_block_reg_launch<T, N, LP, RHS, false, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
 }
 template <class T>
 cudaError_t tri_block_reg(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
                           int64_t rs, int64_t cs, cudaStream_t s) {
-  if (solve) return eff_lower ? tri_block_reg_launch<T, true, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
-                              : tri_block_reg_launch<T, true, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
-  return eff_lower ? tri_block_reg_launch<T, false, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
-                   : tri_block_reg_launch<T, false, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  if (nb <= 64) return tri_block_reg_n<T, 64, 4, 16>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  return tri_block_reg_n<T, 128, 8, 32>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
 }
 
 template <class T, class R, bool SOLVE>
@@ -370,15 +436,22 @@ cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, co
   return e;
 }
 
+/* largest diagonal block launch_tri_block takes: 128 for the real types (register kernel), 64 for the complex ones */
+int tri_block_max(int dtype) {
+  static const bool old_kernel = getenv("B200_TRI_KERNEL") && !strcmp(getenv("B200_TRI_KERNEL"), "smem");
+  return (!old_kernel && (dtype == B200_S || dtype == B200_D)) ? 128 : TRI_NB;
+}
+
 cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,
                              int64_t fs_k, double ar, double ai, void *b, int64_t rs, int64_t cs, cudaStream_t stream) {
   if (nb <= 0 || nrhs <= 0) return cudaSuccess;
-  if (nb > TRI_NB) return cudaErrorInvalidValue;
+  if (nb > tri_block_max(dtype)) return cudaErrorInvalidValue;
   cudaError_t e;
 #define TRI_CASE(T, R) (solve ? tri_block_t<T, R, true>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream) \
                               : tri_block_t<T, R, false>(nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream))
   static const bool old_kernel = getenv("B200_TRI_KERNEL") && !strcmp(getenv("B200_TRI_KERNEL"), "smem");   /* round 1's kernel, for comparison */
   const bool reg_ok = !old_kernel && (rs == 1 || cs == 1);
+  if (!reg_ok && nb > TRI_NB) return cudaErrorInvalidValue;
   switch (dtype) {
     case B200_S: e = reg_ok ? tri_block_reg<float>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(float, float); break;
     case B200_D: e = reg_ok ? tri_block_reg<double>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(double, double); break;

@@ -15,7 +15,7 @@
  *                 plain GEMM straight into C, the NB x NB diagonal block is computed in full into a
  *                 scratch tile and merged under the triangle mask (tri_merge), which also applies
  *                 beta and, for HERK/HER2K, zeroes the diagonal's imaginary part;
- *   TRMM / TRSM   recursive halving of op(A) around one large GEMM per level, 64 x 64 diagonal
+ *   TRMM / TRSM   recursive halving of op(A) around one large GEMM per level, 128 x 128 (real) or 64 x 64 (complex) diagonal
  *                 blocks in tri_block_kernel (see tri_recurse below).
  *
  * Host operands are staged whole (A, B, and the full m x n rectangle of C -- the part of C
@@ -68,7 +68,7 @@ static size_t symm_scratch_bytes(int64_t ka, size_t es) {
  * (the reference blocks the same routines over its GEMM kernel: driver/level3/trmm_L.c, trmm_R.c,
  * trsm_L.c, trsm_R.c).  E is cut at a multiple of 64 near the middle; the off-diagonal block is ONE
  * GEMM with a large inner dimension (that is where the flops are), the two diagonal halves recurse,
- * 64 x 64 diagonal blocks go to tri_block_kernel.  The order of the three steps is what makes the
+ * diagonal blocks of at most tri_block_max() (128 real, 64 complex) go to the block kernels of level3_aux.cu.  The order of the three steps is what makes the
  * update valid in place:
  *   TRMM  left,  E lower:  B2 := a E22 B2;  B2 += a E21 B1;  B1 := a E11 B1      (upper: mirrored)
  *   TRMM  right, E lower:  B1 := a B1 E11;  B1 += a B2 E21;  B2 := a B2 E22
@@ -91,7 +91,8 @@ static cudaError_t tri_gemm(const TriWork &w, int64_t r0, int64_t nr, int64_t c0
 }
 
 static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, double ai) {
-  if (size <= 64) {
+  const int64_t base = tri_block_max(w.dtype);       /* 128 (real types) or 64 */
+  if (size <= base) {
     const bool tr = (w.op & 1) != 0;
     /* left: E(i,k) = op(F)(i,k); right: the kernel works on E^T */
     const int64_t fs_i = (w.left ? tr : !tr) ? w.lda : 1, fs_k = (w.left ? tr : !tr) ? 1 : w.lda;
@@ -100,7 +101,7 @@ static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, d
                         w.left ? w.ldb : 1, w.s));
     return 0;
   }
-  const int64_t s1 = ((size / 2 + 63) / 64) * 64, s2 = size - s1, o2 = off + s1;
+  const int64_t s1 = ((size / 2 + base - 1) / base) * base, s2 = size - s1, o2 = off + s1;
   int err;
   /* which half must be finished first, and which off-diagonal block links them */
   const bool lower_first_is_2 = w.solve ? !w.left : w.left;     /* for E lower: does part 2 go first? */

@@ -200,10 +200,11 @@ cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cud
   count_launch("sim_real_diagonal");
   return cudaSuccess;
 }
+int tri_block_max(int dtype) { return (dtype == B200_S || dtype == B200_D) ? 128 : 64; }
 cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,
                              int64_t fs_k, double ar, double ai, void *b, int64_t rs, int64_t cs, cudaStream_t) {
   if (nb <= 0 || nrhs <= 0) return cudaSuccess;
-  if (nb > 64) return cudaErrorInvalidValue;
+  if (nb > tri_block_max(dtype)) return cudaErrorInvalidValue;
   switch (dtype) {
     case B200_S: tri_block<float>(solve, nb, nrhs, eff_lower, unit, 0, (const float *)f, fs_i, fs_k, (float)ar, (float *)b, rs, cs); break;
     case B200_D: tri_block<double>(solve, nb, nrhs, eff_lower, unit, 0, (const double *)f, fs_i, fs_k, ar, (double *)b, rs, cs); break;
