@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(TRI_RHS * TRI_LANES) tri_block_kernel(int nb, 
  * smaller than 64 are padded with the identity.  Right-hand sides that are rows of B (right side, cs == 1) are read
  * and written straight from global memory, columns of B (rs == 1) through a shared-memory tile. */
 /* two instantiations: 64 x 64 blocks with 4 lanes x 16 rows per right-hand side (16 right-hand sides per 64-thread
- * CTA), and 128 x 128 blocks with 8 lanes x 16 rows (32 per 256-thread CTA): the larger base case removes the deepest
+ * CTA), and 128 x 128 blocks with 8 lanes x 16 rows (64 per 512-thread CTA, so that 8192 right-hand sides are ONE wave of
+ * 128 CTAs: the block is 128 KB of shared memory, one CTA per SM): the larger base case removes the deepest
  * level of the recursion -- 64 GEMMs with k = 64 that ran at 1.4 TFLOP/s (47 us each, profiles/r02_dtrsm8192_launches_*) */
 template <class T> struct Pair2 { T x, y; };
 template <> struct __align__(16) Pair2<double> { double x, y; };
@@ -254,8 +255,12 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
       for (int j = 0; j < BATCH; j++) {
         const int idx = base + j * TRR_THREADS + t;
         const int i = col_major ? idx % N : idx / N, k = col_major ? idx / N : idx % N;
-        E[k * N + i] = (SOLVE && i == k) ? (T)1 / v[j] : v[j];
+        E[k * N + i] = v[j];
       }
+    }
+    if (SOLVE) {                                    /* the N divisions of the whole solve, off the pivot chain */
+      __syncthreads();
+      if (t < N) E[t * N + t] = (T)1 / E[t * N + t];
     }
   }
   /* my rows: CH q + 2 h + e, kept at x[2 q + e] */
@@ -382,7 +387,7 @@ template <class T>
 cudaError_t tri_block_reg(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
                           int64_t rs, int64_t cs, cudaStream_t s) {
   if (nb <= 64) return tri_block_reg_n<T, 64, 4, 16>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
-  return tri_block_reg_n<T, 128, 8, 32>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  return tri_block_reg_n<T, 128, 8, 64>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
 }
 
 template <class T, class R, bool SOLVE>
