@@ -33,9 +33,19 @@ FLOP_FACTOR = {"s": 2.0, "d": 2.0, "c": 8.0, "z": 8.0, "sb": 2.0}   # real flops
 # that file: measured on this pool's B200 with tools/peaks.cu (profiles/r01_peaks_microbench.json):
 # DMMA.8x8x4 issue rate 36.8 TFLOP/s, FFMA 71.1 TFLOP/s (cuBLAS: dgemm 36.0, sgemm-pedantic 66.8).
 PEAK_FALLBACK = {"d": 36.8, "z": 36.8, "s": 71.1, "c": 71.1, "sb": 1590.0}
-# DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from one
-# `ncu --set full` capture of the same shape: profiles/r01_prof_d_16384_final2_summary.txt
-NCU_TRAFFIC_BYTES = {("d", 16384, 16384, 16384): 54.017287e9 + 2.149455e9}
+# DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum): read from the committed
+# summary of one `ncu --set full` capture of the same kernel and shape (profiles/r02_dgemm_16384_ncu.json, written by
+# tools/r02_call14.sh; a number measured under a profiler is evidence about the kernel, never a bench value)
+def ncu_traffic(dtype, m, n, k):
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_dgemm_16384_ncu.json")))
+        if (rec["dtype"], rec["m"], rec["n"], rec["k"]) == (dtype, m, n, k):
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("source", "profiles/r02_dgemm_16384_ncu.json")
+    except Exception:
+        pass
+    if (dtype, m, n, k) == ("d", 16384, 16384, 16384):
+        return 54.017287e9 + 2.149455e9, "profiles/r01_prof_d_16384_final2_summary.txt (round-1 capture of the same kernel)"
+    return None, None
 
 
 _INRUN_PEAKS = None
@@ -445,7 +455,8 @@ def run_gpu(args):
             "dtype": {"d": "f64", "s": "f32", "z": "c128", "c": "c64", "sb": "bf16->f32"}[dtype], "data": "synthetic",
             "config": workload_config(dtype, m, n, k, world, args.nb), "arm": parallelism,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((dtype, m, n, k)) if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         "traffic": ncu_traffic(dtype, m, n, k)[0] if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         "traffic_source": ncu_traffic(dtype, m, n, k)[1] if world == 1 else None,
                          "algorithmic_bytes": (2 if dtype == "sb" else {"s": 4, "d": 8, "c": 8, "z": 16}[dtype]) * (m * k + k * n) + {"s": 4, "d": 8, "c": 8, "z": 16, "sb": 4}[dtype] * m * n,
                          "peak_source": peak_src,
                          "kernel": main_kernel, "kernel_ms_avg": kern_ms_avg if world == 1 else None,

@@ -2,6 +2,7 @@
 the warp-specialised TMA SGEMM / CGEMM (sgemm_ws.cuh), the grouped gemm_batch kernel, the 1-D grid of
 the generic kernel, library shutdown / re-initialisation."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -182,3 +183,76 @@ def test_sbgemm_small_ragged_and_misaligned_shapes_stay_on_tcgen05(ob, oracle):
                     kern = ob.cblas.last_kernel()
                     assert "tcgen05" in kern, (kern, m, n, k, pad, skew)
                     check(oracle, cpu.SB, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, dc.cpu().numpy(), kern)
+
+
+def _summa_bind(lib):
+    lib.b200_summa_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.b200_summa_destroy.argtypes = [C.c_void_p]
+    lib.b200_summa_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.b200_summa_launches.restype = C.c_uint64
+    lib.b200_summa_launches.argtypes = [C.c_void_p]
+    lib.b200_summa_describe.restype = C.c_char_p
+    lib.b200_summa_describe.argtypes = [C.c_void_p]
+    lib.b200_last_error.restype = C.c_char_p
+
+
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.S, cpu.Z, cpu.CX])
+def test_summa_driver_c_abi_on_a_1x1_grid(ob, oracle, dtype):
+    """b200_summa_create / gemm / destroy (include/openblas_b200.h, csrc/summa.cu) through the C ABI on one GPU: the
+    whole machinery -- window packing panel by panel, panels used in place, the double-buffered sweep, k tails,
+    beta on the first panel only, host operands (upload into the window, C strips back), k = 0, window growth -- is
+    the same code that runs on a P x Q grid (tools/summa_c_check.py checks that under torchrun on 2 and 8 GPUs);
+    against the oracle's GEMM."""
+    import torch
+    lib = ob.lib()
+    _summa_bind(lib)
+    h = C.c_void_p()
+    assert lib.b200_summa_create(C.byref(h), bytes(128), 0, 1, 1, 1) == 0, lib.b200_last_error()
+    assert b"1x1" in lib.b200_summa_describe(h)
+    rng = np.random.default_rng(900 + dtype)
+    alphas, betas = alpha_beta(dtype)
+    stream = torch.cuda.current_stream()
+    try:
+        for (m, n, k, nb) in [(300, 260, 200, 64), (130, 77, 513, 128), (64, 64, 0, 32), (1000, 900, 96, 32)]:
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 0, 0, m, n, k, pad=(3, 5, 7))
+            for alpha, beta, where in ((alphas[2], betas[2], "device"), (alphas[1], 0.0, "device"), (alphas[2], betas[2], "host"), (alphas[1], 0.0, "pinned")):
+                start = c0.copy()
+                if beta == 0.0:
+                    start[:, :m] = np.nan                                  # beta == 0 never reads C
+                al, be = ob.cblas.scalar_array(dtype, alpha), ob.cblas.scalar_array(dtype, beta)
+                before = lib.b200_summa_launches(h)
+                if where == "device":
+                    da, db, dc = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(start.copy()).cuda()
+                    rc = lib.b200_summa_gemm(h, dtype, m, n, k, nb, al.ctypes.data, da.data_ptr(), lda, db.data_ptr(), ldb, be.ctypes.data, dc.data_ptr(), ldc,
+                                             stream.cuda_stream)
+                    torch.cuda.synchronize()
+                    got = dc.cpu().numpy()
+                else:
+                    ha, hb, hc = torch.from_numpy(a.copy()), torch.from_numpy(b.copy()), torch.from_numpy(start.copy())
+                    if where == "pinned":
+                        ha, hb, hc = ha.pin_memory(), hb.pin_memory(), hc.pin_memory()
+                    rc = lib.b200_summa_gemm(h, dtype, m, n, k, nb, al.ctypes.data, ha.data_ptr(), lda, hb.data_ptr(), ldb, be.ctypes.data, hc.data_ptr(), ldc,
+                                             stream.cuda_stream)
+                    got = hc.numpy()
+                assert rc == 0, lib.b200_last_error()
+                assert lib.b200_summa_launches(h) - before == max(1, (k + nb - 1) // nb)      # one local product per k panel (k = 0: the scaling of C)
+                check(oracle, dtype, 0, 0, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, got, f"summa-{where}")
+        # illegal calls are refused with a message, not executed
+        assert lib.b200_summa_gemm(h, cpu.SB, 8, 8, 8, 4, None, None, 8, None, 8, None, None, 8, None) != 0
+        assert b"bf16" in lib.b200_last_error()
+    finally:
+        assert lib.b200_summa_destroy(h) == 0
+
+
+def test_summa_driver_on_two_gpus_when_present(ob):
+    """tools/summa_c_check.py under torchrun on 2 GPUs (skipped on a one-GPU box): flags + copy-engine pulls from the
+    peer's window, every rank's block against a one-GPU DGEMM and long-double samples."""
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "summa_c_check.py"), "1500", "1300", "1100", "128"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
