@@ -640,6 +640,13 @@ def run_extras(ob, torch, dev, stream, args):
             r, kern, w = one(dtype, [(0, 0)], size, size, size, 20 if size <= 4096 else 5, check=size <= 4096)
             sw[f"{dtype}gemm_{size}"] = {"tflops": r["NN"], "frac": r["NN"] / peak, "kernel": kern}
     out["square_sweep_nn"] = sw
+    # SBGEMM over sizes (8192^3 is above): small grids leave SMs idle (no split-K), see DESIGN 6a
+    pb = out["sbgemm_8192"]["peak_burst"]
+    sbs = {}
+    for size in (1024, 2048, 4096, 16384):
+        r, kern, w = one("sb", NT4 if size == 4096 else [(0, 0)], size, size, size, 20 if size <= 4096 else 5, check=size <= 4096)
+        sbs[f"sbgemm_{size}"] = {"tflops": r, "frac_of_burst_peak": r["NN"] / pb, "kernel": kern}
+    out["sbgemm_sweep"] = sbs
     return out
 
 
