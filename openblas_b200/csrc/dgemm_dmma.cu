@@ -241,7 +241,7 @@ cudaError_t launch_cfg(const DeviceGemm &g, cudaStream_t stream) {
  * in the main loop, and the producers run ahead across C tiles (the next tile's first stages are in
  * flight during the epilogue).  Two producer warps: one per operand (see produce_operand). */
 template <class C_, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(C_::THREADS + 64, 1)
+__global__ void __launch_bounds__(C_::THREADS + 64, C_::MINB)
 dgemm_dmma_bulk_kernel(DeviceGemm g, int vec_c, int probe_noload) {
   constexpr int BM = C_::BM, BN = C_::BN, BK = C_::BK, LD_K = C_::LD_K, STAGES = C_::STAGES;
   constexpr int FM = C_::FM, FN = C_::FN;
@@ -387,7 +387,8 @@ cudaError_t launch_bulk_variant(const DeviceGemm &g, cudaStream_t stream) {
   }
   int64_t tiles = ((g.m + C_::BM - 1) / C_::BM) * ((g.n + C_::BN - 1) / C_::BN);
   if (g.tri) tiles = tri_tile_count((g.m + C_::BM - 1) / C_::BM);
-  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const int64_t cap = (int64_t)sm_count() * C_::MINB;
+  int grid = (int)(tiles < cap ? tiles : cap);
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 2 == 0);
   static int probe = -1;   /* B200_DGEMM_PROBE_NOLOAD=1: timing probe only, results are garbage */
   if (probe < 0) { const char *e = getenv("B200_DGEMM_PROBE_NOLOAD"); probe = e ? atoi(e) : 0; }
@@ -416,6 +417,7 @@ using CfgBig    = Cfg<128, 128, 32, 32, 16, 4, 1>;   /* 16 warps, 32x32 warp til
 using CfgWide32 = Cfg<128, 128, 64, 32, 32, 3, 1>;   /* as Wide with k step 32: half as many barriers per flop    */
 using CfgWide32b = Cfg<128, 128, 64, 32, 32, 2, 1>;  /* k step 32, double buffer                                  */
 using CfgMid    = Cfg<64, 64, 32, 16, 32, 5, 1>;     /* producer-warp kernel for grids that leave SMs idle at 128x128 */
+using CfgMid2   = Cfg<64, 64, 32, 16, 32, 3, 2>;     /* the same with two CTAs per SM: one CTA's pipeline fill and epilogue hide behind the other's DMMAs */
 
 }  // namespace
 
@@ -440,6 +442,16 @@ cudaError_t launch_dgemm_dmma(const DeviceGemm &g, cudaStream_t stream) {
     const double est128 = 4.0 * (double)((t128 + sms - 1) / sms), est64 = 1.08 * (double)((t64 + sms - 1) / sms);
     const bool small_tile = forced == 64 || (forced != 128 && est64 < est128);
     if (small_tile) {
+      /* two CTAs per SM (3-stage rings) when every tile is resident at once: one CTA's pipeline fill and epilogue hide
+       * behind the other's DMMAs (1024^3: 26.1 -> 27.2 TFLOP/s); with more tiles than 2 x SMs the deeper ring of the
+       * one-CTA form wins (2048^3: 32.7 against 29.4).  B200_DGEMM_MID=1|2 forces one. */
+      static int mid = -1;
+      if (mid < 0) { const char *ev = getenv("B200_DGEMM_MID"); mid = ev ? atoi(ev) : 0; }
+      if (mid == 2 || (mid == 0 && t64 <= 2 * sms)) {
+        e = launch_bulk<CfgMid2>(g, stream);
+        if (e == cudaSuccess) count_launch("dgemm_dmma_pw_64x64x32_w32x16_2cta");
+        return e;
+      }
       e = launch_bulk<CfgMid>(g, stream);
       if (e == cudaSuccess) count_launch("dgemm_dmma_pw_64x64x32_w32x16");
       return e;
