@@ -443,6 +443,11 @@ B200_EXPORT int b200_summa_gemm(b200_summa *h, int dtype, int64_t m, int64_t n, 
   h->count = end;
   CU(cudaEventRecord(h->ev_entry, sc));
   CU(cudaStreamWaitEvent(h->s_pack, h->ev_entry, 0));        /* operands produced on the caller's stream are complete */
+  /* the landing buffers are free again only when the local products of the PREVIOUS call (on the caller's stream) have
+   * read them: without this a fast owner's flag would let the first pulls of this call overwrite a slot under a slow
+   * rank's last product */
+  CU(cudaStreamWaitEvent(h->s_a, h->ev_entry, 0));
+  CU(cudaStreamWaitEvent(h->s_b, h->ev_entry, 0));
   if (h->last_end) {                                          /* my window is free again when every peer finished pulling */
     for (int qq = 0; qq < Q; qq++) if (wait_for(h, h->s_pack, offsetof(Control, done_a), h->rank_of(p, qq), h->last_end)) return 1;
     for (int pp = 0; pp < P; pp++) if (wait_for(h, h->s_pack, offsetof(Control, done_b), h->rank_of(pp, q), h->last_end)) return 1;
