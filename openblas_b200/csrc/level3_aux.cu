@@ -223,12 +223,33 @@ __global__ void __launch_bounds__(TRI_RHS * TRI_LANES) tri_block_kernel(int nb, 
  * CTA), and 128 x 128 blocks with 8 lanes x 16 rows (64 per 512-thread CTA, so that 8192 right-hand sides are ONE wave of
  * 128 CTAs: the block is 128 KB of shared memory, one CTA per SM): the larger base case removes the deepest
  * level of the recursion -- 64 GEMMs with k = 64 that ran at 1.4 TFLOP/s (47 us each, profiles/r02_dtrsm8192_launches_*) */
-template <class T> struct Pair2 { T x, y; };
+template <class T> struct __align__(16) Pair2 { T x, y; };          /* float2 / double2 pairs: 16 / 32 bytes */
 template <> struct __align__(16) Pair2<double> { double x, y; };
 template <> struct __align__(8) Pair2<float> { float x, y; };
+/* x - e * xk and y + e * xk in the working precision (complex: four real FMAs) */
+__device__ __forceinline__ float t_fnma(float e, float xk, float x) { return fmaf(-e, xk, x); }
+__device__ __forceinline__ double t_fnma(double e, double xk, double x) { return fma(-e, xk, x); }
+__device__ __forceinline__ float2 t_fnma(float2 e, float2 xk, float2 x) {
+  x.x = fmaf(-e.x, xk.x, x.x); x.x = fmaf(e.y, xk.y, x.x); x.y = fmaf(-e.x, xk.y, x.y); x.y = fmaf(-e.y, xk.x, x.y); return x;
+}
+__device__ __forceinline__ double2 t_fnma(double2 e, double2 xk, double2 x) {
+  x.x = fma(-e.x, xk.x, x.x); x.x = fma(e.y, xk.y, x.x); x.y = fma(-e.x, xk.y, x.y); x.y = fma(-e.y, xk.x, x.y); return x;
+}
+__device__ __forceinline__ float t_fma(float e, float xk, float y) { return fmaf(e, xk, y); }
+__device__ __forceinline__ double t_fma(double e, double xk, double y) { return fma(e, xk, y); }
+__device__ __forceinline__ float2 t_fma(float2 e, float2 xk, float2 y) {
+  y.x = fmaf(e.x, xk.x, y.x); y.x = fmaf(-e.y, xk.y, y.x); y.y = fmaf(e.x, xk.y, y.y); y.y = fmaf(e.y, xk.x, y.y); return y;
+}
+__device__ __forceinline__ double2 t_fma(double2 e, double2 xk, double2 y) {
+  y.x = fma(e.x, xk.x, y.x); y.x = fma(-e.y, xk.y, y.x); y.y = fma(e.x, xk.y, y.y); y.y = fma(e.y, xk.x, y.y); return y;
+}
+__device__ __forceinline__ float t_shfl_idx(float v, unsigned l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ double t_shfl_idx(double v, unsigned l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ float2 t_shfl_idx(float2 v, unsigned l) { return make_float2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)); }
+__device__ __forceinline__ double2 t_shfl_idx(double2 v, unsigned l) { return make_double2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)); }
 
 template <class T, int N, int LP, int TRR_RHS, bool SOLVE, bool LOWER>
-__global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int64_t nrhs, int unit, const T *__restrict__ f, int64_t fs_i,
+__global__ void __launch_bounds__(LP * TRR_RHS, (LP * TRR_RHS == 256 ? 2 : 1)) tri_block_reg_kernel(int nb, int64_t nrhs, int unit, int cj, const T *__restrict__ f, int64_t fs_i,
                                                                     int64_t fs_k, T alpha, T *__restrict__ b, int64_t rs, int64_t cs) {
   constexpr int TRR_THREADS = LP * TRR_RHS, CH = 2 * LP, NQ = N / CH, NL = N / LP;   /* chunk of rows, chunks, rows per lane */
   extern __shared__ __align__(16) unsigned char tri_smem[];
@@ -249,7 +270,8 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
         const int idx = base + j * TRR_THREADS + t;
         const int i = col_major ? idx % N : idx / N, k = col_major ? idx / N : idx % N;
         const bool diag = i == k, inside = i < nb && k < nb && (LOWER ? (k < i) : (k > i));
-        v[j] = ((diag && !unit && i < nb) || inside) ? f[i * fs_i + k * fs_k] : (diag ? (T)1 : (T)0);
+        v[j] = ((diag && !unit && i < nb) || inside) ? f[i * fs_i + k * fs_k] : (diag ? t_one<T>() : t_zero<T>());
+        if (cj) v[j] = conj_of(v[j]);
       }
 #pragma unroll
       for (int j = 0; j < BATCH; j++) {
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
     }
     if (SOLVE) {                                    /* the N divisions of the whole solve, off the pivot chain */
       __syncthreads();
-      if (t < N) E[t * N + t] = (T)1 / E[t * N + t];
+      if (t < N) E[t * N + t] = t_div(t_one<T>(), E[t * N + t]);
     }
   }
   /* my rows: CH q + 2 h + e, kept at x[2 q + e] */
@@ -269,7 +291,7 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
 #pragma unroll
     for (int l = 0; l < NL; l++) {
       const int r = CH * (l >> 1) + 2 * h + (l & 1);
-      x[l] = (r < nb && c < nrhs) ? b[r * rs + c] : (T)0;
+      x[l] = (r < nb && c < nrhs) ? b[r * rs + c] : t_zero<T>();
     }
     __syncthreads();
   } else {
@@ -279,7 +301,7 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
 #pragma unroll
       for (int j = 0; j < PER; j++) {
         const int idx = j * TRR_THREADS + t, r = idx % N, cc = idx / N;
-        v[j] = (r < nb && c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : (T)0;
+        v[j] = (r < nb && c0 + cc < nrhs) ? b[r * rs + (c0 + cc) * cs] : t_zero<T>();
       }
 #pragma unroll
       for (int j = 0; j < PER; j++) {
@@ -293,17 +315,17 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
   }
   if (SOLVE) {
 #pragma unroll
-    for (int l = 0; l < NL; l++) x[l] *= alpha;
+    for (int l = 0; l < NL; l++) x[l] = t_mul(x[l], alpha);
   } else {
 #pragma unroll
-    for (int l = 0; l < NL; l++) y[l] = (T)0;
+    for (int l = 0; l < NL; l++) y[l] = t_zero<T>();
   }
   const T *Eh = E + 2 * h;
   const unsigned group_base = (unsigned)(t & 31) & ~(unsigned)(LP - 1);
   /* column k of E for my rows of the chunks that still take part; the loads of column k + 1 are issued before the
    * updates of column k (ptxas keeps only a few of them in flight; with 8 per column that is enough) */
   Pair2<T> ecur[NQ], enext[NQ];
-  T dcur = (T)1, dnext = (T)1;
+  T dcur = t_one<T>(), dnext = t_one<T>();
   auto load_column = [&](Pair2<T> (&e)[NQ], T &d, int k) {
     const int kq = k / CH;
 #pragma unroll
@@ -318,8 +340,8 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
     const int kq = k / CH, kh = (k % CH) >> 1, kl = 2 * kq + (k & 1);      /* chunk, owner lane of the group, owner's slot of row k */
     if (kk + 1 < N) load_column(enext, dnext, LOWER ? k + 1 : k - 1);
     T xk = x[kl];
-    if (SOLVE) xk *= dcur;
-    xk = __shfl_sync(0xffffffffu, xk, group_base | (unsigned)kh);
+    if (SOLVE) xk = t_mul(xk, dcur);
+    xk = t_shfl_idx(xk, group_base | (unsigned)kh);
     if (SOLVE && h == kh) x[kl] = xk;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
@@ -328,12 +350,12 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
       if (SOLVE) {
         /* rows strictly beyond the pivot; only the pivot's own chunk needs the test */
         const bool on0 = q != kq || (LOWER ? r0 > k : r0 < k), on1 = q != kq || (LOWER ? r0 + 1 > k : r0 + 1 < k);
-        if (on0) x[2 * q] = fma(-ecur[q].x, xk, x[2 * q]);
-        if (on1) x[2 * q + 1] = fma(-ecur[q].y, xk, x[2 * q + 1]);
+        if (on0) x[2 * q] = t_fnma(ecur[q].x, xk, x[2 * q]);
+        if (on1) x[2 * q + 1] = t_fnma(ecur[q].y, xk, x[2 * q + 1]);
       } else {
         const bool on0 = q != kq || (LOWER ? r0 >= k : r0 <= k), on1 = q != kq || (LOWER ? r0 + 1 >= k : r0 + 1 <= k);
-        if (on0) y[2 * q] = fma(ecur[q].x, xk, y[2 * q]);
-        if (on1) y[2 * q + 1] = fma(ecur[q].y, xk, y[2 * q + 1]);
+        if (on0) y[2 * q] = t_fma(ecur[q].x, xk, y[2 * q]);
+        if (on1) y[2 * q + 1] = t_fma(ecur[q].y, xk, y[2 * q + 1]);
       }
     }
 #pragma unroll
@@ -342,7 +364,7 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
   }
   if (!SOLVE) {
 #pragma unroll
-    for (int l = 0; l < NL; l++) x[l] = alpha * y[l];
+    for (int l = 0; l < NL; l++) x[l] = t_mul(alpha, y[l]);
   }
   if (cs == 1) {
 #pragma unroll
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(LP * TRR_RHS) tri_block_reg_kernel(int nb, int
 }
 
 template <class T, int N, int LP, int RHS, bool SOLVE, bool LOWER>
-cudaError_t tri_block_reg_launch(int nb, int64_t nrhs, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b, int64_t rs,
+cudaError_t tri_block_reg_launch(int nb, int64_t nrhs, int unit, int cj, const void *f, int64_t fs_i, int64_t fs_k, T alpha, void *b, int64_t rs,
                                  int64_t cs, cudaStream_t s) {
   static bool configured = false;
   auto kern = tri_block_reg_kernel<T, N, LP, RHS, SOLVE, LOWER>;
@@ -372,22 +394,29 @@ cudaError_t tri_block_reg_launch(int nb, int64_t nrhs, int unit, const void *f, 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<(unsigned)((nrhs + RHS - 1) / RHS), LP * RHS, smem, s>>>(nb, nrhs, unit, (const T *)f, fs_i, fs_k, (T)ar, (T *)b, rs, cs);
+  kern<<<(unsigned)((nrhs + RHS - 1) / RHS), LP * RHS, smem, s>>>(nb, nrhs, unit, cj, (const T *)f, fs_i, fs_k, alpha, (T *)b, rs, cs);
   return cudaGetLastError();
 }
 template <class T, int N, int LP, int RHS>
-cudaError_t tri_block_reg_n(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
-                            int64_t rs, int64_t cs, cudaStream_t s) {
-  if (solve) return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, true, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
-                              : tri_block_reg_launch<T, N, LP, RHS, true, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
-  return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, false, true>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s)
-                   : tri_block_reg_launch<T, N, LP, RHS, false, false>(nb, nrhs, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+cudaError_t tri_block_reg_n(int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i, int64_t fs_k, T alpha,
+                            void *b, int64_t rs, int64_t cs, cudaStream_t s) {
+  if (solve) return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, true, true>(nb, nrhs, unit, cj, f, fs_i, fs_k, alpha, b, rs, cs, s)
+                              : tri_block_reg_launch<T, N, LP, RHS, true, false>(nb, nrhs, unit, cj, f, fs_i, fs_k, alpha, b, rs, cs, s);
+  return eff_lower ? tri_block_reg_launch<T, N, LP, RHS, false, true>(nb, nrhs, unit, cj, f, fs_i, fs_k, alpha, b, rs, cs, s)
+                   : tri_block_reg_launch<T, N, LP, RHS, false, false>(nb, nrhs, unit, cj, f, fs_i, fs_k, alpha, b, rs, cs, s);
 }
 template <class T>
 cudaError_t tri_block_reg(int solve, int nb, int64_t nrhs, int eff_lower, int unit, const void *f, int64_t fs_i, int64_t fs_k, double ar, void *b,
                           int64_t rs, int64_t cs, cudaStream_t s) {
-  if (nb <= 64) return tri_block_reg_n<T, 64, 4, 16>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
-  return tri_block_reg_n<T, 128, 8, 64>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, s);
+  if (nb <= 64) return tri_block_reg_n<T, 64, 4, 16>(solve, nb, nrhs, eff_lower, unit, 0, f, fs_i, fs_k, (T)ar, b, rs, cs, s);
+  return tri_block_reg_n<T, 128, 8, 64>(solve, nb, nrhs, eff_lower, unit, 0, f, fs_i, fs_k, (T)ar, b, rs, cs, s);
+}
+/* complex: 64 x 64 blocks, 8 lanes x 8 rows per right-hand side, 32 right-hand sides per 256-thread CTA (two CTAs per SM) */
+template <class T, class R>
+cudaError_t tri_block_reg_cplx(int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i, int64_t fs_k, double ar,
+                               double ai, void *b, int64_t rs, int64_t cs, cudaStream_t s) {
+  T alpha; alpha.x = (R)ar; alpha.y = (R)ai;
+  return tri_block_reg_n<T, 64, 8, 32>(solve, nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, alpha, b, rs, cs, s);
 }
 
 template <class T, class R, bool SOLVE>
@@ -460,8 +489,8 @@ cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff
   switch (dtype) {
     case B200_S: e = reg_ok ? tri_block_reg<float>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(float, float); break;
     case B200_D: e = reg_ok ? tri_block_reg<double>(solve, nb, nrhs, eff_lower, unit, f, fs_i, fs_k, ar, b, rs, cs, stream) : TRI_CASE(double, double); break;
-    case B200_C: e = TRI_CASE(float2, float); break;
-    case B200_Z: e = TRI_CASE(double2, double); break;
+    case B200_C: e = reg_ok ? tri_block_reg_cplx<float2, float>(solve, nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream) : TRI_CASE(float2, float); break;
+    case B200_Z: e = reg_ok ? tri_block_reg_cplx<double2, double>(solve, nb, nrhs, eff_lower, unit, cj, f, fs_i, fs_k, ar, ai, b, rs, cs, stream) : TRI_CASE(double2, double); break;
     default: return cudaErrorNotSupported;
   }
 #undef TRI_CASE
