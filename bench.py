@@ -482,11 +482,11 @@ def run_gpu(args):
         print(json.dumps(out))
 
 
-def sampled_parity(torch, dtype, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, samples=64, alpha=1.0, seed=7):
-    """`samples` entries of C = alpha * op(A) op(B) (beta = 0) recomputed on the host in long double from the
+def sampled_parity(torch, dtype, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, samples=64, alpha=1.0, seed=7, beta=0.0, c0=None):
+    """`samples` entries of C = alpha * op(A) op(B) + beta * C0 recomputed on the host in long double from the
     operands as they lie in HBM, outside every timed region.  Returns the worst ratio
-    |C - C_ref| / (k * eps * sum|a||b|): the north-star acceptance bound is ratio <= c with c = 2.
-    Column-major operands held as 2-D torch tensors (cols, ld)."""
+    |C - C_ref| / (k * eps * (|alpha| sum|a||b| + |beta||c0|)): the north-star acceptance bound is ratio <= c with
+    c = 2.  Column-major operands held as 2-D torch tensors (cols, ld); c0 = the C the call started from (beta != 0)."""
     import numpy as np
     g = torch.Generator(); g.manual_seed(seed)
     ii = torch.randint(0, m, (samples,), generator=g).tolist()
@@ -515,9 +515,13 @@ def sampled_parity(torch, dtype, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, sample
             bc = np.conj(bc)
         ref = alpha * np.dot(ar, bc)
         gauge = float(abs(alpha) * np.dot(np.abs(ar), np.abs(bc)))
+        if beta != 0.0:
+            old = ld_t(c0[j, i].item())
+            ref = ref + ld_t(beta) * old
+            gauge += float(abs(beta) * abs(old))
         got = c[j, i].item()
         worst = max(worst, float(abs(ld_t(got) - ref)) / (k * eps * gauge))
-    return {"worst_ratio": worst, "samples": samples, "bound": "|C - C_ref| <= 2 * k * eps * (|A||B|) per entry, C_ref in long double on the host",
+    return {"worst_ratio": worst, "samples": samples, "bound": "|C - C_ref| <= 2 * k * eps * (|alpha||A||B| + |beta||C|) per entry, C_ref in long double on the host",
             "ok": worst <= 2.0}
 
 
@@ -553,17 +557,21 @@ def run_extras(ob, torch, dev, stream, args):
             return torch.rand((cols, rows), generator=gen, device=dev, dtype=torch.float32).sub_(0.5).to(t)
         return torch.rand((cols, rows), generator=gen, device=dev, dtype=t).sub_(0.5)
 
-    def one(dtype, ops, m, n, k, reps, check=True):
-        """every op combination in `ops` on an m x n x k problem; returns {op: TFLOP/s (real flops)}, kernel, parity"""
+    def one(dtype, ops, m, n, k, reps, check=True, alpha=1.0, beta=0.0):
+        """every op combination in `ops` on an m x n x k problem; returns {op: TFLOP/s (real flops)}, kernel, parity.
+        beta != 0: the timed calls keep updating C in place; the checked call starts again from a saved C0 (when C is
+        too big to keep a second copy -- the 64 GiB C of the tall-skinny shape -- the check is a beta = 0 call)."""
         code = DT[dtype]
         res, worst, kern = {}, 0.0, None
         odt = torch.float32 if dtype == "sb" else T[dtype]
-        c = torch.empty((n, m), dtype=odt, device=dev)
+        keep_c0 = beta != 0.0 and n * m * ES[dtype] <= (8 << 30)
+        c = rand(n, m, dtype) if (beta != 0.0 and dtype != "sb") else torch.empty((n, m), dtype=odt, device=dev)
+        c0 = c.clone() if keep_c0 else None
         for ta, tb in ops:
             ra, ca = (k, m) if ta & 1 else (m, k)
             rb, cb = (n, k) if tb & 1 else (k, n)
             a, b = rand(ca, ra, dtype), rand(cb, rb, dtype)
-            f = lambda: ob.cblas.gemm_device(code, ta, tb, m, n, k, 1.0, a, ra, b, rb, 0.0, c, m, stream.cuda_stream)
+            f = lambda al=alpha, be=beta: ob.cblas.gemm_device(code, ta, tb, m, n, k, al, a, ra, b, rb, be, c, m, stream.cuda_stream)
             for _ in range(3):
                 f()
             torch.cuda.synchronize(dev)
@@ -571,9 +579,16 @@ def run_extras(ob, torch, dev, stream, args):
             res["NTRC"[ta] + "NTRC"[tb]] = FLOP_FACTOR[dtype] * m * n * k / (ms * 1e-3) / 1e12
             kern = ob.cblas.last_kernel()
             if check:
-                worst = max(worst, sampled_parity(torch, dtype, ta, tb, m, n, k, a, ra, b, rb, c, m, samples=16)["worst_ratio"])
+                if keep_c0:
+                    c.copy_(c0); f(); torch.cuda.synchronize(dev)
+                    w = sampled_parity(torch, dtype, ta, tb, m, n, k, a, ra, b, rb, c, m, samples=16, alpha=alpha, beta=beta, c0=c0)
+                else:
+                    if beta != 0.0:
+                        f(alpha, 0.0); torch.cuda.synchronize(dev)
+                    w = sampled_parity(torch, dtype, ta, tb, m, n, k, a, ra, b, rb, c, m, samples=16, alpha=alpha)
+                worst = max(worst, w["worst_ratio"])
             del a, b
-        del c
+        del c, c0
         return res, kern, worst
 
     out = {}
@@ -608,12 +623,16 @@ def run_extras(ob, torch, dev, stream, args):
     time.sleep(3.0)      # let the power state settle before the FP32 / FP64 measurements
 
     # (b) FP32 / complex at the sizes the targets are quoted on
-    for key, dtype, size, ops, reps in (("sgemm_16384", "s", 16384, NT4, 3), ("zgemm_8192", "z", 8192, NT4 + [(3, 0), (3, 3)], 3),
-                                        ("cgemm_8192", "c", 8192, NT4 + [(3, 0), (3, 3)], 3)):
+    # complex: BASELINE config 5 -- all nine N/T/C combinations, alpha = (0.7, -0.9), beta = (1.3, -1.1) (ctest/zin3:11-13)
+    NTC9 = [(x, y) for y in (0, 1, 3) for x in (0, 1, 3)]
+    CA, CB_ = 0.7 - 0.9j, 1.3 - 1.1j
+    for key, dtype, size, ops, reps in (("sgemm_16384", "s", 16384, NT4, 3), ("zgemm_8192", "z", 8192, NTC9, 3), ("cgemm_8192", "c", 8192, NTC9, 3)):
         peak, src = measured_peak(dtype, dev.index or 0)
-        r, kern, w = one(dtype, ops, size, size, size, reps)
+        cplx = dtype in ("z", "c")
+        r, kern, w = one(dtype, ops, size, size, size, reps, alpha=CA if cplx else 1.0, beta=CB_ if cplx else 0.0)
         out[key] = {"tflops_real_flops": r, "tflops_2mnk": {o: v * 2.0 / FLOP_FACTOR[dtype] for o, v in r.items()}, "kernel": kern, "peak": peak,
-                    "frac": r["NN"] / peak, "worst_op": min(r, key=r.get), "worst_op_frac": min(r.values()) / peak, "parity_worst_ratio": w}
+                    "frac": r["NN"] / peak, "worst_op": min(r, key=r.get), "worst_op_frac": min(r.values()) / peak, "parity_worst_ratio": w,
+                    "alpha_beta": "(0.7,-0.9), (1.3,-1.1)" if cplx else "1, 0"}
     out["peak_source_fp32"] = measured_peak("s", dev.index or 0)[1]
 
     # (c) BASELINE config 5, tall-skinny: flop bound and HBM bound side by side (algorithmic bytes = A + B + C once)
@@ -621,8 +640,8 @@ def run_extras(ob, torch, dev, stream, args):
     for dtype in ("z", "c"):
         peak, _ = measured_peak(dtype, dev.index or 0)
         for (mm, nn, kk) in ((65536, 256, 65536), (65536, 65536, 256)):
-            r, kern, w = one(dtype, [(0, 0), (3, 0)] if nn == 256 else [(0, 0)], mm, nn, kk, 3)
-            bytes_alg = ES[dtype] * (mm * kk + kk * nn + mm * nn)
+            r, kern, w = one(dtype, [(0, 0), (3, 0)] if nn == 256 else [(0, 0)], mm, nn, kk, 3, alpha=CA, beta=CB_)
+            bytes_alg = ES[dtype] * (mm * kk + kk * nn + 2 * mm * nn)          # beta != 0: C is read and written
             flops = FLOP_FACTOR[dtype] * mm * nn * kk
             t_flop, t_hbm = flops / (peak * 1e12), (bytes_alg / (hbm * 1e9)) if hbm else None
             ts[f"{dtype}gemm_{mm}x{nn}x{kk}"] = {"tflops_real_flops": r, "tflops_2mnk": {o: v * 2.0 / FLOP_FACTOR[dtype] for o, v in r.items()}, "kernel": kern,
@@ -636,7 +655,7 @@ def run_extras(ob, torch, dev, stream, args):
     sw = {}
     for dtype in ("d", "s"):
         peak, _ = measured_peak(dtype, dev.index or 0)
-        for size in (1024, 2048, 4096, 8192):
+        for size in (1024, 2048, 4096, 8192, 12288):
             r, kern, w = one(dtype, [(0, 0)], size, size, size, 20 if size <= 4096 else 5, check=size <= 4096)
             sw[f"{dtype}gemm_{size}"] = {"tflops": r["NN"], "frac": r["NN"] / peak, "kernel": kern}
     out["square_sweep_nn"] = sw
