@@ -604,3 +604,43 @@ def test_gemmt_block_column_scheme_and_device_operands(sim, oracle, monkeypatch)
                     cpu.call_gemmt(sim, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, got, ldc)
                     want, gauge, mk = F.gemmt_expected(oracle, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c0, ldc, False)
                     F.check_gemmt(dtype, m, k, ldc, got, want, gauge, mk, c0, (tri_env, dtype, uplo, ta, tb))
+
+
+def test_sbgemv_sbdot_on_device_operands_use_the_callers_increments(sim, oracle):
+    """"device" operands (hostsim allocations) are used in place: no staging copies, the kernel stand-in sees the
+    caller's increments (negative ones walk from the far end); mixed host / device operands stage only the host ones."""
+    rng = np.random.default_rng(21)
+    m, n, lda = 37, 23, 40
+    a = oracle.tobf16(rng.random((n, lda), dtype=np.float32) - 0.5)
+    for trans in (0, 1):
+        lenx, leny = (m, n) if trans else (n, m)
+        for incx, incy in ((1, 1), (-2, 3), (3, -1)):
+            x = oracle.tobf16(rng.random(1 + (lenx - 1) * abs(incx), dtype=np.float32) - 0.5)
+            y0 = (rng.random(1 + (leny - 1) * abs(incy)) - 0.5).astype(np.float32)
+            want = y0.copy()
+            oracle.sbgemv(trans, m, n, 0.7, a, lda, x, incx, 1.3, want, incy)
+            for mix in ("all", "a only", "y only"):
+                da = sim.hostsim_device_alloc(a.nbytes); C.memmove(da, a.ctypes.data, a.nbytes)
+                dx = sim.hostsim_device_alloc(x.nbytes); C.memmove(dx, x.ctypes.data, x.nbytes)
+                dy = sim.hostsim_device_alloc(y0.nbytes); C.memmove(dy, y0.ctypes.data, y0.nbytes)
+                hy = y0.copy()
+                pa = da if mix in ("all", "a only") else a
+                px = dx if mix == "all" else x
+                py = dy if mix in ("all", "y only") else hy
+                before = sim.hostsim_copy_count()
+                cpu.call_sbgemv(sim, trans, m, n, 0.7, pa, lda, px, incx, 1.3, py, incy, cblas=(mix == "all"))
+                copies = sim.hostsim_copy_count() - before
+                got = np.empty_like(y0)
+                if mix in ("all", "y only"):
+                    C.memmove(got.ctypes.data, dy, got.nbytes)
+                else:
+                    got = hy
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (trans, incx, incy, mix)
+                if mix == "all":
+                    assert copies == 0, copies
+                for p in (da, dx, dy):
+                    sim.hostsim_free(p)
+    x = oracle.tobf16(rng.random(50, dtype=np.float32) - 0.5)
+    dx = sim.hostsim_device_alloc(x.nbytes); C.memmove(dx, x.ctypes.data, x.nbytes)
+    assert np.float32(cpu.call_sbdot(sim, 25, dx, 2, x, -1)) == np.float32(oracle.sbdot(25, x, 2, x, -1)[0])
+    sim.hostsim_free(dx)
