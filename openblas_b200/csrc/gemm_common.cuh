@@ -48,6 +48,28 @@ __host__ __device__ __forceinline__ void tri_tile_coords(int64_t u, int tri, int
   const int64_t c = u - r * (r + 1) / 2;
   if (tri == 1) { bm = r; bn = c; } else { bm = c; bn = r; }
 }
+/* Tiles twice as tall as wide (the warp-specialised S/CGEMM kernel: 256 x 128, complex 128 x 64), tm x tn of them over
+ * a square window (tn = 2 tm or 2 tm - 1): tile (bm, bn) has an element in the lower triangle iff bn <= 2 bm + 1, in
+ * the upper one iff bn >= 2 bm.  The lower triangle is enumerated row by row (row r holds min(tn, 2 r + 2) tiles,
+ * r (r + 1) before it), the upper one column by column (column c holds c / 2 + 1 tiles; q (q + 1) before column 2 q,
+ * (q + 1)^2 before column 2 q + 1).  Walking ALL tiles and skipping, as round 1 did for rectangular tiles, leaves the
+ * static round-robin over persistent CTAs unbalanced by a tile or two per CTA out of seven (SSYRK 8192: 47 TFLOP/s
+ * against 61 for the GEMM). */
+__host__ __device__ __forceinline__ int64_t tri21_tile_count(int tri, int64_t tm, int64_t tn) {
+  if (tri == 1) { const int64_t full = tm * (tm + 1), over = 2 * tm - tn; return full - (over > 0 ? over : 0); }
+  const int64_t q = tn / 2;
+  return (tn & 1) ? (q + 1) * (q + 1) : q * (q + 1);
+}
+__host__ __device__ __forceinline__ void tri21_tile_coords(int64_t u, int tri, int64_t &bm, int64_t &bn) {
+  int64_t q = (int64_t)((sqrt(4.0 * (double)u + 1.0) - 1.0) * 0.5);
+  while (q * (q + 1) > u) q--;
+  while ((q + 1) * (q + 2) <= u) q++;
+  if (tri == 1) { bm = q; bn = u - q * (q + 1); return; }
+  if (u >= (q + 1) * (q + 1)) { bn = 2 * q + 1; bm = u - (q + 1) * (q + 1); } else { bn = 2 * q; bm = u - q * (q + 1); }
+}
+/* tiles twice as WIDE as tall (the ZGEMM kernel: 64 x 128): the transposed picture of the above */
+__host__ __device__ __forceinline__ int64_t tri12_tile_count(int tri, int64_t tm, int64_t tn) { return tri21_tile_count(3 - tri, tn, tm); }
+__host__ __device__ __forceinline__ void tri12_tile_coords(int64_t u, int tri, int64_t &bm, int64_t &bn) { tri21_tile_coords(u, 3 - tri, bn, bm); }
 __host__ __device__ __forceinline__ bool tri_keep(int tri, int64_t m, int64_t n) {
   return tri == 1 ? m >= n : tri == 2 ? m <= n : true;
 }

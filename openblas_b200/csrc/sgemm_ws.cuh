@@ -101,7 +101,7 @@ struct TileWalk {
   __device__ __forceinline__ void init(const DeviceGemm &g) {
     tiles_m = (g.m + BM - 1) / BM; tiles_n = (g.n + BN - 1) / BN;
     tri = g.tri;
-    tiles = (tri && BM == BN) ? tri_tile_count(tiles_m) : tiles_m * tiles_n;
+    tiles = (tri && BM == BN) ? tri_tile_count(tiles_m) : (tri && BM == 2 * BN) ? tri21_tile_count(tri, tiles_m, tiles_n) : tiles_m * tiles_n;
     t = (int64_t)blockIdx.x - (int64_t)gridDim.x;
   }
   /* next tile of this CTA; false when there is none */
@@ -110,7 +110,9 @@ struct TileWalk {
       t += gridDim.x;
       if (t >= tiles) return false;
       int64_t bm, bn;
-      if (tri && BM == BN) tri_tile_coords(t, tri, bm, bn); else banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
+      if (tri && BM == BN) tri_tile_coords(t, tri, bm, bn);
+      else if (tri && BM == 2 * BN) tri21_tile_coords(t, tri, bm, bn);
+      else banded_tile_coords<16>(t, tiles_m, tiles_n, bm, bn);
       m0 = bm * BM; n0 = bn * BN;
       if (!tri_outside(tri, m0, BM, n0, BN)) return true;
     }
@@ -469,7 +471,7 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream) {
                    : make_map_f32(&map_b, g.b, (uint64_t)g.k * EM, (uint64_t)g.n, pb, C::BK * EM, C::BN / EM, stage_swz));
   if (!ok) return cudaErrorNotSupported;
   const int64_t tm = (g.m + C::BM / EM - 1) / (C::BM / EM), tn = (g.n + C::BN / EM - 1) / (C::BN / EM);
-  const int64_t tiles = (g.tri && C::BM == C::BN) ? tri_tile_count(tm) : tm * tn;
+  const int64_t tiles = (g.tri && C::BM == C::BN) ? tri_tile_count(tm) : (g.tri && C::BM == 2 * C::BN) ? tri21_tile_count(g.tri, tm, tn) : tm * tn;
   const int64_t cap = (int64_t)sm_count() * C::MINB;
   const int grid = (int)(tiles < cap ? tiles : cap);
   const int vec_c = (((uintptr_t)g.c & 15) == 0) && ((g.ldc * 4 * EM) % 16 == 0);

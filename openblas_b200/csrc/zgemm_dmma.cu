@@ -199,7 +199,11 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
   const double2 *__restrict__ B = (const double2 *)g.b;
   double2 *__restrict__ C = (double2 *)g.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const int64_t tiles_m = (g.m + BM - 1) / BM, tiles_n = (g.n + BN - 1) / BN;
+  /* triangle (SYRK family, GEMMT): only the tiles that touch it are enumerated (BN == 2 BM: tri12_tile_coords), so the
+   * static round-robin over persistent CTAs stays balanced; round 1 walked all tiles and skipped */
+  static_assert(BN == 2 * BM, "tri12 enumeration assumes tiles twice as wide as tall");
+  const int64_t tiles = g.tri ? tri12_tile_count(g.tri, tiles_m, tiles_n) : tiles_m * tiles_n;
   const int64_t ktiles = (g.k + BK - 1) / BK;
 
   if (tid == 0) {
@@ -213,9 +217,9 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
     int slot = 0; uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       int64_t bm, bn;
-      banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+      if (g.tri) tri12_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
       const int64_t m0 = bm * BM, n0 = bn * BN;
-      if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* consumers skip the same tiles */
+      if (tri_outside(g.tri, m0, BM, n0, BN)) continue;      /* (never on the triangle's own enumeration) */
       for (int64_t kt = 0; kt < ktiles; kt++) {
         mbar_wait(empty_bar(slot), phase ^ 1);
         const uint32_t sa = smem_base + (uint32_t)(slot * STAGE_ELEMS * 16), sb = sa + (uint32_t)(A_ELEMS * 16);
@@ -242,7 +246,7 @@ zgemm_dmma_pw_kernel(DeviceGemm g) {
   int slot = 0; uint32_t phase = 0;
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     int64_t bm, bn;
-    banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
+    if (g.tri) tri12_tile_coords(t, g.tri, bm, bn); else banded_tile_coords<32>(t, tiles_m, tiles_n, bm, bn);
     const int64_t m0 = bm * BM, n0 = bn * BN;
     if (tri_outside(g.tri, m0, BM, n0, BN)) continue;
 

@@ -46,6 +46,45 @@ int main() {
         if (tri_outside(tri, bm * 64, 64, bn * 128, 128) != !any) failures++;
         if (any && tri_partial(tri, bm * 64, 64, bn * 128, 128) != !all) failures++;
       }
+  // tiles twice as tall as wide (256 x 128): the compact enumeration visits exactly the tiles that are not "outside", once each
+  for (int tri = 1; tri <= 2; tri++)
+    for (int64_t n = 1; n <= 40 * 128; n += 61) {
+      const int64_t tm = (n + 255) / 256, tn = (n + 127) / 128;
+      std::vector<char> seen((size_t)(tm * tn), 0);
+      const int64_t T = tri21_tile_count(tri, tm, tn);
+      for (int64_t u = 0; u < T; u++) {
+        int64_t bm, bn;
+        tri21_tile_coords(u, tri, bm, bn);
+        if (bm < 0 || bn < 0 || bm >= tm || bn >= tn || seen[(size_t)(bm * tn + bn)] || tri_outside(tri, bm * 256, 256, bn * 128, 128)) { failures++; continue; }
+        seen[(size_t)(bm * tn + bn)] = 1;
+      }
+      for (int64_t bm = 0; bm < tm; bm++)
+        for (int64_t bn = 0; bn < tn; bn++)
+          if (!tri_outside(tri, bm * 256, 256, bn * 128, 128) && !seen[(size_t)(bm * tn + bn)]) failures++;
+    }
+  // tiles twice as wide as tall (64 x 128, the ZGEMM kernel): same property through the transposed enumeration
+  for (int tri = 1; tri <= 2; tri++)
+    for (int64_t n = 1; n <= 40 * 128; n += 53) {
+      const int64_t tm = (n + 63) / 64, tn = (n + 127) / 128;
+      std::vector<char> seen((size_t)(tm * tn), 0);
+      const int64_t T = tri12_tile_count(tri, tm, tn);
+      for (int64_t u = 0; u < T; u++) {
+        int64_t bm, bn;
+        tri12_tile_coords(u, tri, bm, bn);
+        if (bm < 0 || bn < 0 || bm >= tm || bn >= tn || seen[(size_t)(bm * tn + bn)] || tri_outside(tri, bm * 64, 64, bn * 128, 128)) { failures++; continue; }
+        seen[(size_t)(bm * tn + bn)] = 1;
+      }
+      for (int64_t bm = 0; bm < tm; bm++)
+        for (int64_t bn = 0; bn < tn; bn++)
+          if (!tri_outside(tri, bm * 64, 64, bn * 128, 128) && !seen[(size_t)(bm * tn + bn)]) failures++;
+    }
+  for (int64_t r : {(int64_t)1 << 20, ((int64_t)1 << 29) + 777}) {
+    int64_t bm, bn;
+    tri21_tile_coords(r * (r + 1) + 5, 1, bm, bn);
+    if (bm != r || bn != 5) failures++;
+    tri21_tile_coords((r + 1) * (r + 1) + 3, 2, bm, bn);
+    if (bn != 2 * r + 1 || bm != 3) failures++;
+  }
   printf(failures ? "TRI TILES: %d FAILURES\n" : "TRI TILES OK (%d failures)\n", failures);
   return failures != 0;
 }
