@@ -222,7 +222,7 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream, int vec_a, 
   return cudaGetLastError();
 }
 
-typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true> CwsConfig;
+typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true, false, true> CwsConfig;
 
 }  // namespace
 

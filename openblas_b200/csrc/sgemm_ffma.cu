@@ -487,9 +487,10 @@ cudaError_t launch_ops(const DeviceGemm &g, cudaStream_t stream, int vec_a, int 
 }
 
 /* 8 consumer warps (2 x 4, warp tile 128 x 32, 16 x 8 per thread, 224 registers via setmaxnreg) + a producer
- * warpgroup (one feeder warp per operand, 56 registers), 5-stage ring of 24 KB stages, fragments of the next
- * stage prefetched under the last FMA block of the current one. */
-typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true> WsConfig;
+ * warpgroup (one feeder warp per operand plus one helper warp each for the transposition of k-contiguous tiles, 56
+ * registers), 5-stage ring of 24 KB stages, fragments of the next stage prefetched under the last FMA block of the
+ * current one. */
+typedef sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true, false, true> WsConfig;
 
 }  // namespace
 

@@ -71,9 +71,12 @@ __device__ __forceinline__ void mbar_wait_ws(uint32_t bar, uint32_t parity) { mb
 /* PW = 1: one extra producer warp, every warp keeps the launch register count.  PW = 4: a whole producer
  * warpgroup (only its first warp works) so that setmaxnreg can move registers: producers shrink to RP,
  * the consumer warpgroups grow to RC (8 * CONSUMERS * RC + 4 * RP must not exceed the CTA's launch pool). */
-template <int TM_, int WARPS_M_, int WARPS_N_, int STAGES_, int MINB_, int STG_ = 2, int PW_ = 1, int RC_ = 0, int RP_ = 0, bool XPF_ = false, bool SNAKE_ = false>
+/* HELP (needs PW = 4): the two spare warps of the producer warpgroup each take half of the rows of a staged
+ * (k-contiguous) tile, so the register -> shared transposition of one stage is shared by two warps per operand (ncu:
+ * with one warp the consumers spent 4 % of their time waiting for full[] in NN, nothing in NT) */
+template <int TM_, int WARPS_M_, int WARPS_N_, int STAGES_, int MINB_, int STG_ = 2, int PW_ = 1, int RC_ = 0, int RP_ = 0, bool XPF_ = false, bool SNAKE_ = false, bool HELP_ = false>
 struct Cfg {
-  static constexpr bool XPF = XPF_, SNAKE = SNAKE_;
+  static constexpr bool XPF = XPF_, SNAKE = SNAKE_, HELP = HELP_ && PW_ == 4;
   static_assert(!XPF_ || (16 % 2 == 0), "XPF needs an even BK (fragment buffers alternate)");
   static constexpr int PW = PW_, RC = RC_, RP = RP_;
   static_assert(PW == 1 || (PW == 4 && (WARPS_M_ * WARPS_N_) % 4 == 0), "setmaxnreg works on whole warpgroups");
@@ -85,7 +88,7 @@ struct Cfg {
   static constexpr int BM = WARPS_M * WM, BN = WARPS_N * WN;
   static constexpr int STAGES = STAGES_, MINB = MINB_, STG = STG_;
   static constexpr int A_FLOATS = BM * BK, B_FLOATS = BN * BK, STAGE_FLOATS = A_FLOATS + B_FLOATS;
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 2 * STG);
+  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4 * STG);      /* full, empty, staging landed (2 operands), staging consumed (2 operands) */
   static constexpr int FEEDERS = PW_ == 4 ? 2 : 1;          /* producer warps that actually work */
   static_assert(TM % 4 == 0 && BM <= 256 && BN <= 256, "TMA boxes are at most 256 elements per dimension");
   static constexpr size_t smem_bytes(bool a_mn, bool b_mn) {
@@ -120,11 +123,12 @@ struct TileWalk {
 };
 
 /* producer warp: staging tile [ROWS][16 floats], 64B-swizzled by TMA  ->  S[k][mn] (row stride ROWS floats) */
-template <int ROWS, bool CPLX>
+template <int ROWS, bool CPLX, int PART = 0>
 __device__ __forceinline__ void transpose_staged(const float *stg, float *dst, int lane) {
+  constexpr int RB = ROWS / 32, RB0 = PART == 2 ? RB / 2 : 0, RB1 = PART == 1 ? RB / 2 : RB;
   if (!CPLX) {
 #pragma unroll
-    for (int rb = 0; rb < ROWS / 32; rb++) {
+    for (int rb = RB0; rb < RB1; rb++) {
       const int row = rb * 32 + lane;
       const int sw = (row >> 1) & 3;                       /* Swizzle<2,4,3>: 16-byte chunk ^= address bits 7..8 */
       float4 v[4];
@@ -143,7 +147,7 @@ __device__ __forceinline__ void transpose_staged(const float *stg, float *dst, i
      * interleaved (re, im): 8-byte elements move as STS.64 */
     float2 *d2 = reinterpret_cast<float2 *>(dst);
 #pragma unroll
-    for (int rb = 0; rb < ROWS / 32; rb++) {
+    for (int rb = RB0; rb < RB1; rb++) {
       const int row = rb * 32 + lane;
       const int sw = row & 7;
 #pragma unroll
@@ -185,12 +189,14 @@ sgemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto stg_bar = [&](int w, int s) { return bars + 8u * (2 * STAGES + w * STG + s); };
+  auto stg_free = [&](int w, int s) { return bars + 8u * (2 * STAGES + 2 * STG + w * STG + s); };     /* HELP: the helper is done with staging buffer s */
+  constexpr int HELPERS = C::HELP ? ((A_MN ? 0 : 1) + (B_MN ? 0 : 1)) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ktiles = (g.k + BK - 1) / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), C::FEEDERS); mbar_init(empty_bar(s), C::CONSUMERS); }
-    for (int s = 0; s < 2 * STG; s++) mbar_init(stg_bar(0, s), 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), C::FEEDERS + HELPERS); mbar_init(empty_bar(s), C::CONSUMERS); }
+    for (int s = 0; s < 4 * STG; s++) mbar_init(stg_bar(0, s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -206,6 +212,25 @@ sgemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
      * registers. */
     if (C::RP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::RP ? C::RP : 24));
     const int pw = warp - C::CONSUMERS;
+    if (C::HELP && pw >= 2) {
+      /* helper of feeder pw - 2: the second half of the rows of every staged tile of that operand */
+      const int pf = pw - 2;
+      if ((pf == 0 && A_MN) || (pf == 1 && B_MN)) return;
+      uint32_t it = 0;
+      int64_t m0, n0;
+      while (walk.next(m0, n0)) {
+        for (int64_t kt = 0; kt < ktiles; kt++, it++) {
+          const int slot = (int)(it % STAGES), j = (int)(it % STG);
+          mbar_wait_ws(empty_bar(slot), ((it / STAGES) & 1) ^ 1);
+          mbar_wait_ws(stg_bar(pf, j), (it / STG) & 1);
+          if (pf == 0) transpose_staged<TILE_M, CPLX, 2>(stg_a + j * A_FLOATS, ring + slot * STAGE_FLOATS, lane);
+          else transpose_staged<TILE_N, CPLX, 2>(stg_b + j * B_FLOATS, ring + slot * STAGE_FLOATS + A_FLOATS, lane);
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(full_bar(slot)); mbar_arrive(stg_free(pf, j)); }
+        }
+      }
+      return;
+    }
     if (pw >= C::FEEDERS) return;
     const bool do_a = C::FEEDERS == 1 || pw == 0, do_b = C::FEEDERS == 1 || pw == 1;
     const bool stage_a = do_a && !A_MN, stage_b = do_b && !B_MN;
@@ -220,6 +245,7 @@ sgemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     auto stage_next = [&]() {                             /* issue the staging copies of the next k tile of `ahead` */
       if (!staged_bytes) return;
       if (!ahead_ok || akt >= ktiles) { ahead_ok = ahead.next(am0, an0); akt = 0; if (!ahead_ok) return; }
+      if (C::HELP && stg_issue >= (uint32_t)STG) mbar_wait_ws(stg_free(pw, (int)(stg_issue % STG)), ((stg_issue / STG) - 1) & 1);   /* the helper has read the buffer's previous tile */
       if (lane == 0) {
         const int j = (int)(stg_issue % STG);
         mbar_expect_tx(stg_bar(pw, j), staged_bytes);
@@ -247,8 +273,8 @@ sgemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (staged_bytes) {
           const int j = (int)(it % STG);
           mbar_wait_ws(stg_bar(pw, j), (it / STG) & 1);
-          if (stage_a) transpose_staged<TILE_M, CPLX>(stg_a + j * A_FLOATS, ring + slot * STAGE_FLOATS, lane);
-          if (stage_b) transpose_staged<TILE_N, CPLX>(stg_b + j * B_FLOATS, ring + slot * STAGE_FLOATS + A_FLOATS, lane);
+          if (stage_a) transpose_staged<TILE_M, CPLX, C::HELP ? 1 : 0>(stg_a + j * A_FLOATS, ring + slot * STAGE_FLOATS, lane);
+          if (stage_b) transpose_staged<TILE_N, CPLX, C::HELP ? 1 : 0>(stg_b + j * B_FLOATS, ring + slot * STAGE_FLOATS + A_FLOATS, lane);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(slot));

@@ -70,6 +70,10 @@ static Variant variants[] = {
     {"ws TM8  4x4 256x128 S5 rc112 xpf", sws::launch<sws::Cfg<8, 4, 4, 5, 1, 2, 4, 112, 32, true>>},
     {"ws TM8  3x4 192x128 S5 pw1 xpf", sws::launch<sws::Cfg<8, 3, 4, 5, 1, 2, 1, 0, 0, true>>},
     {"ws TM16 2x4 256x128 S6 pw1 (168 regs)", sws::launch<sws::Cfg<16, 2, 4, 6, 1>>},
+    {"ws TM16 2x4 S5 rc224 xpf (library r2a)", sws::launch<sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true>>},
+    {"ws TM16 2x4 S5 rc224 xpf HELP", sws::launch<sws::Cfg<16, 2, 4, 5, 1, 2, 4, 224, 56, true, false, true>>},
+    {"ws TM16 2x4 S5 STG3 rc224 xpf HELP", sws::launch<sws::Cfg<16, 2, 4, 5, 1, 3, 4, 224, 56, true, false, true>>},
+    {"ws TM16 2x4 S4 STG3 rc224 xpf HELP", sws::launch<sws::Cfg<16, 2, 4, 4, 1, 3, 4, 224, 56, true, false, true>>},
 };
 
 int main(int argc, char **argv) {
