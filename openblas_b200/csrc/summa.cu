@@ -488,13 +488,20 @@ B200_EXPORT int b200_summa_gemm(b200_summa *h, int dtype, int64_t m, int64_t n, 
   }
   CU(cudaStreamWaitEvent(sc, h->ev_cup, 0));
 
-  /* ---- the sweep ------------------------------------------------------------------------------------------ */
-  auto fetch = [&](int64_t s, int slot, const char **a_pan, const char **b_pan) -> int {
+  /* ---- the sweep ------------------------------------------------------------------------------------------
+   * A host C is swept in two column halves (each one through all k panels): the first half goes back to the host
+   * while the second one is computed, so only half of the download is exposed at the end.  The A panels are pulled
+   * again for the second half (the windows still hold them; a pull costs a few per cent of a local product). */
+  /* B200_SUMMA_HOST_HALVES: 0 = one sweep always; n > 1 = smallest local column count that is split (default 8192; tests lower it) */
+  static const int64_t halves_from = getenv("B200_SUMMA_HOST_HALVES") ? (atoll(getenv("B200_SUMMA_HOST_HALVES")) == 1 ? 8192 : atoll(getenv("B200_SUMMA_HOST_HALVES"))) : 8192;
+  const int nsweeps = (c_host && halves_from > 0 && h->transport == TRANSPORT_PULL && n_loc >= halves_from && steps >= 2) ? 2 : 1;
+  auto fetch = [&](int64_t s, int slot, int64_t J0, int64_t J1, const char **a_pan, const char **b_pan) -> int {
     const int64_t w = k - s * nb < nb ? k - s * nb : nb;
     const int qa = (int)(s % Q), pb = (int)(s % P);
     const int64_t ca = (s / Q) * nb, rb = (s / P) * nb;
     char *la = h->land + (size_t)slot * (a_slot + b_slot), *lb = la + a_slot;
-    const size_t a_bytes = (size_t)m_loc * (size_t)w * es, b_bytes = (size_t)w * (size_t)n_loc * es;
+    const size_t a_bytes = (size_t)m_loc * (size_t)w * es, b_bytes = (size_t)w * (size_t)(J1 - J0) * es;
+    const size_t b_at = b_off + ((size_t)rb * (size_t)n_loc + (size_t)J0 * (size_t)w) * es;      /* columns J0.. of the dense w x n_loc panel */
     if (h->transport == TRANSPORT_PULL) {
       const int ra = h->rank_of(p, qa), rbk = h->rank_of(pb, q);
       if (qa == q) { *a_pan = h->win + (size_t)ca * (size_t)m_loc * es; CU(cudaStreamWaitEvent(h->s_a, h->ev_pack_a[(size_t)(s / Q)], 0)); }
@@ -503,10 +510,10 @@ B200_EXPORT int b200_summa_gemm(b200_summa *h, int dtype, int64_t m, int64_t n, 
         if (a_bytes) CU(cudaMemcpyAsync(la, h->peer_win[(size_t)ra] + (size_t)ca * (size_t)m_loc * es, a_bytes, cudaMemcpyDefault, h->s_a));
         *a_pan = la;
       }
-      if (pb == p) { *b_pan = h->win + b_off + (size_t)rb * (size_t)n_loc * es; CU(cudaStreamWaitEvent(h->s_b, h->ev_pack_b[(size_t)(s / P)], 0)); }
+      if (pb == p) { *b_pan = h->win + b_at; CU(cudaStreamWaitEvent(h->s_b, h->ev_pack_b[(size_t)(s / P)], 0)); }
       else {
         if (wait_for(h, h->s_b, offsetof(Control, packed_b), rbk, base + (uint32_t)(s / P) + 1)) return 1;
-        if (b_bytes) CU(cudaMemcpyAsync(lb, h->peer_win[(size_t)rbk] + b_off + (size_t)rb * (size_t)n_loc * es, b_bytes, cudaMemcpyDefault, h->s_b));
+        if (b_bytes) CU(cudaMemcpyAsync(lb, h->peer_win[(size_t)rbk] + b_at, b_bytes, cudaMemcpyDefault, h->s_b));
         *b_pan = lb;
       }
     } else {
@@ -515,47 +522,54 @@ B200_EXPORT int b200_summa_gemm(b200_summa *h, int dtype, int64_t m, int64_t n, 
       *a_pan = la; *b_pan = lb;
       if (Q > 1) { if (a_bytes) NC(g_nccl.Broadcast(h->win + (size_t)ca * (size_t)m_loc * es, la, a_bytes, ncclInt8, qa, h->row_comm, h->s_a)); }
       else *a_pan = h->win + (size_t)ca * (size_t)m_loc * es;
-      if (P > 1) { if (b_bytes) NC(g_nccl.Broadcast(h->win + b_off + (size_t)rb * (size_t)n_loc * es, lb, b_bytes, ncclInt8, pb, h->col_comm, h->s_a)); }
-      else *b_pan = h->win + b_off + (size_t)rb * (size_t)n_loc * es;
+      if (P > 1) { if (b_bytes) NC(g_nccl.Broadcast(h->win + b_at, lb, b_bytes, ncclInt8, pb, h->col_comm, h->s_a)); }
+      else *b_pan = h->win + b_at;
     }
     CU(cudaEventRecord(h->ev_a[slot], h->s_a));
     CU(cudaEventRecord(h->ev_b[slot], h->s_b));
     return 0;
   };
 
-  const char *a_pan[2] = {nullptr, nullptr}, *b_pan[2] = {nullptr, nullptr};
   const bool pulls = work || h->transport == TRANSPORT_NCCL;     /* broadcasts are collective even for a rank with no C */
-  if (steps > 0 && pulls && fetch(0, 0, &a_pan[0], &b_pan[0])) return 1;
-  for (int64_t s = 0; s < steps; s++) {
-    const int slot = (int)(s & 1);
-    if (s + 1 < steps && pulls) {
-      const int ns = (int)((s + 1) & 1);
-      if (s >= 1) { CU(cudaStreamWaitEvent(h->s_a, h->ev_free[ns], 0)); CU(cudaStreamWaitEvent(h->s_b, h->ev_free[ns], 0)); }
-      if (fetch(s + 1, ns, &a_pan[ns], &b_pan[ns])) return 1;
+  for (int v = 0; v < nsweeps; v++) {
+    const int64_t J0 = n_loc * v / nsweeps, J1 = n_loc * (v + 1) / nsweeps, nj = J1 - J0;
+    const char *a_pan[2] = {nullptr, nullptr}, *b_pan[2] = {nullptr, nullptr};
+    if (v > 0) {                      /* both landing slots are free again when the previous sweep's last products have read them */
+      for (int sl = 0; sl < 2; sl++) { CU(cudaStreamWaitEvent(h->s_a, h->ev_free[sl], 0)); CU(cudaStreamWaitEvent(h->s_b, h->ev_free[sl], 0)); }
     }
-    if (!work) continue;
-    const int64_t w = k - s * nb < nb ? k - s * nb : nb;
-    CU(cudaStreamWaitEvent(sc, h->ev_a[slot], 0));
-    CU(cudaStreamWaitEvent(sc, h->ev_b[slot], 0));
-    const void *bs = s == 0 ? beta : one;
-    if (c_host && s + 1 == steps) {
-      /* last update of a host C: column strips, each downloaded while the next one is computed */
-      const int strips = n_loc >= 4096 ? 4 : 1;
-      for (int t = 0; t < strips; t++) {
-        const int64_t j0 = n_loc * t / strips, j1 = n_loc * (t + 1) / strips;
-        if (b200::summa_local_gemm(dtype, m_loc, j1 - j0, w, alpha, a_pan[slot], m_loc, b_pan[slot] + (size_t)j0 * (size_t)w * es, w, bs,
-                                   c_dev + (size_t)j0 * (size_t)ldc_dev * es, ldc_dev, sc)) return 1;
-        h->launches++;
-        CU(cudaEventRecord(h->ev_strip[t & 1], sc));
-        CU(cudaStreamWaitEvent(h->s_out, h->ev_strip[t & 1], 0));
-        if (copy2d((char *)c_loc + (size_t)j0 * (size_t)ldc * es, (size_t)ldc * es, c_dev + (size_t)j0 * (size_t)ldc_dev * es, (size_t)ldc_dev * es,
-                   (size_t)m_loc * es, (size_t)(j1 - j0), h->s_out)) return 1;
+    if (steps > 0 && pulls && fetch(0, 0, J0, J1, &a_pan[0], &b_pan[0])) return 1;
+    for (int64_t s = 0; s < steps; s++) {
+      const int slot = (int)(s & 1);
+      if (s + 1 < steps && pulls) {
+        const int ns = (int)((s + 1) & 1);
+        if (s >= 1) { CU(cudaStreamWaitEvent(h->s_a, h->ev_free[ns], 0)); CU(cudaStreamWaitEvent(h->s_b, h->ev_free[ns], 0)); }
+        if (fetch(s + 1, ns, J0, J1, &a_pan[ns], &b_pan[ns])) return 1;
       }
-    } else {
-      if (b200::summa_local_gemm(dtype, m_loc, n_loc, w, alpha, a_pan[slot], m_loc, b_pan[slot], w, bs, c_dev, ldc_dev, sc)) return 1;
-      h->launches++;
+      if (!work) continue;
+      const int64_t w = k - s * nb < nb ? k - s * nb : nb;
+      CU(cudaStreamWaitEvent(sc, h->ev_a[slot], 0));
+      CU(cudaStreamWaitEvent(sc, h->ev_b[slot], 0));
+      const void *bs = s == 0 ? beta : one;
+      char *c_sweep = c_dev + (size_t)J0 * (size_t)ldc_dev * es;
+      if (c_host && s + 1 == steps) {
+        /* last update of these columns of a host C: strips, each downloaded while the next one is computed */
+        const int strips = nj >= 4096 ? 4 : 1;
+        for (int t = 0; t < strips; t++) {
+          const int64_t j0 = nj * t / strips, j1 = nj * (t + 1) / strips;
+          if (b200::summa_local_gemm(dtype, m_loc, j1 - j0, w, alpha, a_pan[slot], m_loc, b_pan[slot] + (size_t)j0 * (size_t)w * es, w, bs,
+                                     c_sweep + (size_t)j0 * (size_t)ldc_dev * es, ldc_dev, sc)) return 1;
+          h->launches++;
+          CU(cudaEventRecord(h->ev_strip[t & 1], sc));
+          CU(cudaStreamWaitEvent(h->s_out, h->ev_strip[t & 1], 0));
+          if (copy2d((char *)c_loc + (size_t)(J0 + j0) * (size_t)ldc * es, (size_t)ldc * es, c_sweep + (size_t)j0 * (size_t)ldc_dev * es,
+                     (size_t)ldc_dev * es, (size_t)m_loc * es, (size_t)(j1 - j0), h->s_out)) return 1;
+        }
+      } else {
+        if (b200::summa_local_gemm(dtype, m_loc, nj, w, alpha, a_pan[slot], m_loc, b_pan[slot], w, bs, c_sweep, ldc_dev, sc)) return 1;
+        h->launches++;
+      }
+      CU(cudaEventRecord(h->ev_free[slot], sc));
     }
-    CU(cudaEventRecord(h->ev_free[slot], sc));
   }
   if (steps == 0 && work) {           /* k == 0: C := beta * C */
     if (b200::summa_local_gemm(dtype, m_loc, n_loc, 0, alpha, c_dev, ldc_dev, c_dev, ldc_dev, beta, c_dev, ldc_dev, sc)) return 1;

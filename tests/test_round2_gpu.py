@@ -256,3 +256,16 @@ def test_summa_driver_on_two_gpus_when_present(ob):
                         "--master-port", "29533", os.path.join(root, "tools", "summa_c_check.py"), "1500", "1300", "1100", "128"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
+
+
+def test_summa_driver_host_c_in_two_column_sweeps(ob):
+    """A host C is swept in two column halves so that the first half's download hides behind the second half's products
+    (default from 8192 local columns; B200_SUMMA_HOST_HALVES lowers the limit, read once per process, hence the child):
+    tools/summa_c_check.py on one GPU with host operands -- pinned, pageable, beta != 0 -- against a one-GPU DGEMM and
+    long-double samples."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200_SUMMA_HOST_HALVES="64")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "summa_c_check.py"), "1000", "900", "800", "128"], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
