@@ -271,6 +271,16 @@ void cgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, flo
 void zgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, double *alpha, double *a, blasint *ldA, double *b,
              blasint *ldB, double *beta, double *c, blasint *ldC);
 
+/* ---- SBGEMMT: ?GEMMT with bf16 A and B, fp32 alpha, beta and C (interface/sbgemmt.c:47-52 Fortran,
+ *      :143-149 CBLAS; built under BUILD_BFLOAT16, interface/Makefile:52,290,1306,1970; the reference declares it in
+ *      no public header).  One triangle-masked launch of the tcgen05 SBGEMM kernel.  As in the reference: K == 0
+ *      leaves C untouched whatever beta is, and a RowMajor call does NOT flip Uplo (sbgemmt.c:239-240). */
+void cblas_sbgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
+                   blasint M, blasint K, float alpha, const bfloat16 *A, blasint lda, const bfloat16 *B, blasint ldb,
+                   float beta, float *C, blasint ldc);
+void sbgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, float *alpha, bfloat16 *a, blasint *ldA,
+              bfloat16 *b, blasint *ldB, float *beta, float *c, blasint *ldC);
+
 /* ---- SBGEMV / SBDOT: bf16 operands, fp32 accumulation and result (cblas.h:441-442;
  *      common_interface.h:62,258; interface/sbgemv.c, interface/bf16dot.c, kernel/x86_64/sbgemv_n.c, sbgemv_t.c,
  *      sbdot.c).  HBM-bound CUDA kernels (csrc/bf16_level12.cu), deterministic (no atomics). */

@@ -141,21 +141,24 @@ static void rankk_entry(const char *name, int routine, int dtype, int cblas, int
  * (Fortran) / :232-262 (CBLAS); row-major = the column-major problem with A and B swapped and uplo flipped (:305-345);
  * checks :163-186 column-major, :365-389 row-major -- the row-major branch reports positions 10 / 8 for the leading
  * dimensions it calls lda / ldb (the caller's LDB / LDA; the 10 test comes last) and 3 / 2 for the trans flags;
- * xerbla_ gets sizeof("?GEMMT ") = 8; quick return m == 0 (:464).  The reference then walks the triangle column by
+ * xerbla_ gets sizeof("?GEMMT ") = 8; quick return m == 0 (:464).  SBGEMMT (interface/sbgemmt.c) comes through here too.  The reference then walks the triangle column by
  * column with GEMV (and conjugates its "b" operand IN PLACE for transb = R / C, :466-476, never undoing it -- not
  * reproduced: inputs are const here); here it is ONE triangle-masked launch of the GEMM kernel. */
 static void gemmt_entry(const char *name, int dtype, int cblas, int order, int uplo, int transa, int transb, int64_t m,
                         int64_t k, const double alpha[2], const void *a, int64_t lda, const void *b, int64_t ldb,
                         const double beta[2], void *c, int64_t ldc) {
   blasint info = cblas ? -1 : 0;
-  char nm[9];
-  memcpy(nm, name, 8);
-  nm[8] = 0;
+  const int sb = dtype == B200_SB;
+  const blasint name_len = (blasint)strlen(name) + 1;      /* sizeof(ERROR_NAME): 8, or 9 for "SBGEMMT " */
+  char nm[10];
+  memcpy(nm, name, (size_t)name_len);
   if (cblas && order == CblasRowMajor) {
     const void *t = a; a = b; b = t;
     int64_t tl = lda; lda = ldb; ldb = tl;
     int tt = transa; transa = transb; transb = tt;
-    uplo = flip(uplo);
+    /* interface/sbgemmt.c:239-240 keeps uplo as given (gemmt.c:322-323 flips it), so a row-major SBGEMMT updates the
+     * other triangle of the caller's C than a row-major ?GEMMT would: reproduced, callers of the reference see this */
+    if (!sb) uplo = flip(uplo);
     const int64_t ncola = (transa >= 0 && (transa & 1)) ? k : m, ncolb = (transb >= 0 && (transb & 1)) ? m : k;
     if (ldc < max1(m)) info = 13;
     if (ldb < max1(ncolb)) info = 8;
@@ -178,8 +181,11 @@ static void gemmt_entry(const char *name, int dtype, int cblas, int order, int u
     if (transa < 0) info = 2;
     if (uplo < 0) info = 1;
   }
-  if (cblas ? info >= 0 : info != 0) { xerbla_(nm, &info, 8); return; }
+  if (cblas ? info >= 0 : info != 0) { xerbla_(nm, &info, name_len); return; }
   if (m == 0) return;
+  /* SBGEMMT hands every column to the SBGEMV kernel, which returns at once for an empty dimension
+   * (kernel/x86_64/sbgemv_n.c:114): k == 0 leaves C as it is, whatever beta says */
+  if (sb && k == 0) return;
 
   b200_l3_problem p;
   memset(&p, 0, sizeof p);
@@ -357,3 +363,20 @@ DEF_GEMMT(sgemmt, "SGEMMT ", B200_S, 0, float, float, SC_REAL, float)
 DEF_GEMMT(dgemmt, "DGEMMT ", B200_D, 0, double, double, SC_REAL, double)
 DEF_GEMMT(cgemmt, "CGEMMT ", B200_C, 1, void, const void *, SC_CF, float)
 DEF_GEMMT(zgemmt, "ZGEMMT ", B200_Z, 1, void, const void *, SC_CD, double)
+
+/* SBGEMMT (interface/sbgemmt.c; built with BUILD_BFLOAT16, interface/Makefile:52,290; declared in no public header
+ * of the reference): bf16 A and B, fp32 alpha, beta and C; checks and info numbers as ?GEMMT (:121-137, :286-301),
+ * xerbla_ gets sizeof("SBGEMMT ") = 9 */
+B200_EXPORT void cblas_sbgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA,
+                               enum CBLAS_TRANSPOSE TransB, blasint M, blasint K, float alpha, const bfloat16 *A, blasint lda,
+                               const bfloat16 *B, blasint ldb, float beta, float *C, blasint ldc) {
+  const double al[2] = {alpha, 0.0}, be[2] = {beta, 0.0};
+  gemmt_entry("SBGEMMT ", B200_SB, 1, (int)Order, uplo_of_cblas((int)Uplo), op_of_cblas((int)TransA, 0), op_of_cblas((int)TransB, 0),
+              M, K, al, A, lda, B, ldb, be, C, ldc);
+}
+B200_EXPORT void sbgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, float *alpha, bfloat16 *a, blasint *ldA,
+                          bfloat16 *b, blasint *ldB, float *beta, float *c, blasint *ldC) {
+  const double al[2] = {*alpha, 0.0}, be[2] = {*beta, 0.0};
+  gemmt_entry("SBGEMMT ", B200_SB, 0, 0, uplo_of_char(*UPLO), op_of_char(*TRANSA, 0), op_of_char(*TRANSB, 0), *M, *K, al, a, *ldA,
+              b, *ldB, be, c, *ldC);
+}

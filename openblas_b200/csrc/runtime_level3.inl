@@ -178,10 +178,13 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
   const bool two = p->routine == B200_SYR2K || p->routine == B200_HER2K;
   const bool gemmt = p->routine == B200_GEMMT;
   const int64_t n = p->n, k = p->k;
+  /* SBGEMMT: bf16 factors (es = 2), fp32 C: C addresses, the scratch tile and the merge are fp32's */
+  const size_t esc = b200_out_size(p->dtype);
+  const int merge_dtype = p->dtype == B200_SB ? B200_S : p->dtype;
   const bool product = k > 0 && !alpha_zero;
   if (!product) {                      /* only the triangle is scaled; beta == 1 leaves C alone */
     if (br == 1.0 && bi == 0.0) return 0;
-    CK(launch_tri_merge(p->dtype, p->uplo, herm, n, nullptr, 0, br, bi, c, ldc, s));
+    CK(launch_tri_merge(merge_dtype, p->uplo, herm, n, nullptr, 0, br, bi, c, ldc, s));
     return 0;
   }
   /* first factor op(X) (rows of C), second factor op(Y)^T or op(Y)^H (columns of C):
@@ -216,12 +219,12 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
   }
 
   const int64_t nb = rankk_block(n);
-  const int64_t ldt = (int64_t)(round_up((size_t)nb * es, 128) / es);
+  const int64_t ldt = (int64_t)(round_up((size_t)nb * esc, 128) / esc);
   for (int64_t j0 = 0; j0 < n; j0 += nb) {
     const int64_t jb = n - j0 < nb ? n - j0 : nb;
     /* rectangle inside the triangle: rows below the diagonal block (lower) or above it (upper) */
     const int64_t i0 = p->uplo ? j0 + jb : 0, mr = p->uplo ? n - j0 - jb : j0;
-    char *c_rect = c + ((size_t)i0 + (size_t)j0 * (size_t)ldc) * es;
+    char *c_rect = c + ((size_t)i0 + (size_t)j0 * (size_t)ldc) * esc;
     if (mr > 0) {
       CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai, at(a, lda, i0), lda, at2(y1, ldy1, j0), ldy1, br, bi, c_rect, ldc, s));
       if (two) CK(gemm_on_device(p->dtype, op_first, op_second, mr, jb, k, ar, ai2, at(b, ldb, i0), ldb, at2(a, lda, j0), lda, 1.0, 0.0,
@@ -231,7 +234,7 @@ static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda
     CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai, at(a, lda, j0), lda, at2(y1, ldy1, j0), ldy1, 0.0, 0.0, scratch, ldt, s));
     if (two) CK(gemm_on_device(p->dtype, op_first, op_second, jb, jb, k, ar, ai2, at(b, ldb, j0), ldb, at2(a, lda, j0), lda, 1.0, 0.0,
                                scratch, ldt, s));
-    CK(launch_tri_merge(p->dtype, p->uplo, herm, jb, scratch, ldt, br, bi, c + ((size_t)j0 + (size_t)j0 * (size_t)ldc) * es, ldc, s));
+    CK(launch_tri_merge(merge_dtype, p->uplo, herm, jb, scratch, ldt, br, bi, c + ((size_t)j0 + (size_t)j0 * (size_t)ldc) * esc, ldc, s));
   }
   return 0;
 }
@@ -248,7 +251,8 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   if (!product && beta_one && !trxm) return 0;
 
   Operand A, B, C;
-  A.es = B.es = C.es = es;
+  A.es = B.es = es;
+  C.es = b200_out_size(p->dtype);      /* differs from es only for SBGEMMT (bf16 in, fp32 out) */
   if (symm || trxm) {
     const int64_t ka = p->side ? p->n : p->m;
     A.rows = A.cols = ka; B.rows = p->m; B.cols = p->n;
@@ -281,7 +285,7 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
   size_t scratch_bytes = 0;
   if (product && !trxm) {
     const int64_t edge = rankk_block(p->n);
-    scratch_bytes = symm ? symm_scratch_bytes(A.rows, es) : round_up(round_up((size_t)edge * es, 128) * (size_t)edge, 256);
+    scratch_bytes = symm ? symm_scratch_bytes(A.rows, es) : round_up(round_up((size_t)edge * C.es, 128) * (size_t)edge, 256);
   }
   int err = reserve_device(ctx, need + scratch_bytes);
   if (err) return err;

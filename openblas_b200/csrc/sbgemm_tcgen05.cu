@@ -141,10 +141,27 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   bn = r / rows;
 }
 
+/* SBGEMMT (DeviceGemm::tri = 1 lower / 2 upper, M == N): the persistent loops walk only the tiles that hold an element
+ * of the triangle -- the closed-form enumerations of gemm_common.cuh, WIDE for the 128 x 256 tiles of the single-CTA
+ * kernel, square for the 256 x 256 tiles of the CTA pairs -- and the epilogue masks the stores of the tiles the
+ * diagonal crosses.  Half the tiles, half the time; the untouched triangle of C is neither read nor written. */
+template <bool WIDE>
+__host__ __device__ __forceinline__ int tile_count_for(int tri, int tiles_m, int tiles_n) {
+  if (!tri) return tiles_m * tiles_n;
+  return (int)(WIDE ? tri12_tile_count(tri, tiles_m, tiles_n) : tri_tile_count(tiles_m));
+}
+template <bool WIDE>
+__device__ __forceinline__ void tile_coords_for(int t, int tri, int tiles_m, int tiles_n, int &bm, int &bn) {
+  if (!tri) { tile_coords(t, tiles_m, tiles_n, bm, bn); return; }
+  int64_t r, c;
+  if (WIDE) tri12_tile_coords(t, tri, r, c); else tri_tile_coords(t, tri, r, c);
+  bm = (int)r; bn = (int)c;
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 sbgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      float *__restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
+                      float *__restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta, int tri) {
   extern __shared__ uint8_t raw_smem[];
   const uint32_t base = (smem_u32(raw_smem) + 1023u) & ~1023u;     /* SWIZZLE_128B needs 1024-byte alignment */
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -157,7 +174,7 @@ sbgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int tiles = tiles_m * tiles_n;
+  const int tiles = tile_count_for<true>(tri, tiles_m, tiles_n);
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -181,7 +198,7 @@ sbgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       int bm, bn;
-      tile_coords(t, tiles_m, tiles_n, bm, bn);
+      tile_coords_for<true>(t, tri, tiles_m, tiles_n, bm, bn);
       const int m0 = bm * BLOCK_M, n0 = bn * BLOCK_N;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
@@ -248,7 +265,7 @@ sbgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int local = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, local++) {
       int bm, bn;
-      tile_coords(t, tiles_m, tiles_n, bm, bn);
+      tile_coords_for<true>(t, tri, tiles_m, tiles_n, bm, bn);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int64_t m = (int64_t)bm * BLOCK_M + quarter * 32 + lane;
@@ -265,7 +282,7 @@ sbgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           float *p = C + m + (n0 + c) * ldc;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            if (n0 + c + j < N) {
+            if (n0 + c + j < N && tri_keep(tri, m, n0 + c + j)) {
               float v = alpha * __uint_as_float(r[j]);
               if (use_beta) v = fmaf(beta, p[(int64_t)j * ldc], v);
               p[(int64_t)j * ldc] = v;
@@ -351,7 +368,7 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(bool a_mn, bool b_mn) {
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 sbgemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                           float *__restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
+                           float *__restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta, int tri) {
   constexpr int STAGES = two::STAGES;
   constexpr uint32_t A_BYTES = two::A_BYTES, STAGE_BYTES = two::STAGE_BYTES;
   extern __shared__ uint8_t raw_smem[];
@@ -368,7 +385,7 @@ sbgemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int tiles_m = (M + two::TILE_M - 1) / two::TILE_M, tiles_n = (N + two::TILE_N - 1) / two::TILE_N;
-  const int tiles = tiles_m * tiles_n;
+  const int tiles = tile_count_for<false>(tri, tiles_m, tiles_n);
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
@@ -393,7 +410,7 @@ sbgemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
     int stage = 0; uint32_t phase = 0;
     for (int t = cluster_id; t < tiles; t += num_clusters) {
       int bm, bn;
-      tile_coords(t, tiles_m, tiles_n, bm, bn);
+      tile_coords_for<false>(t, tri, tiles_m, tiles_n, bm, bn);
       const int m0 = bm * two::TILE_M + (int)rank * 128, n0 = bn * two::TILE_N + (int)rank * 128;
       for (int kb = 0; kb < num_kb; kb++) {
         if (lane == 0) {
@@ -460,7 +477,7 @@ sbgemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
     int local = 0;
     for (int t = cluster_id; t < tiles; t += num_clusters, local++) {
       int bm, bn;
-      tile_coords(t, tiles_m, tiles_n, bm, bn);
+      tile_coords_for<false>(t, tri, tiles_m, tiles_n, bm, bn);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int64_t m = (int64_t)bm * two::TILE_M + rank * 128 + quarter * 32 + lane;
@@ -477,7 +494,7 @@ sbgemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
           float *p = C + m + (n0 + c) * ldc;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            if (n0 + c + j < N) {
+            if (n0 + c + j < N && tri_keep(tri, m, n0 + c + j)) {
               float v = alpha * __uint_as_float(r[j]);
               if (use_beta) v = fmaf(beta, p[(int64_t)j * ldc], v);
               p[(int64_t)j * ldc] = v;
@@ -546,10 +563,10 @@ cudaError_t launch_variant(const DeviceGemm &g, cudaStream_t stream) {
   ok = ok && (B_MN ? make_map(&map_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, 64, BLOCK_K)
                    : make_map(&map_b, g.b, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.ldb, BLOCK_K, BLOCK_N));
   if (!ok) return cudaErrorNotSupported;
-  int tiles = (int)(((g.m + BLOCK_M - 1) / BLOCK_M) * ((g.n + BLOCK_N - 1) / BLOCK_N));
+  int tiles = tile_count_for<true>(g.tri, (int)((g.m + BLOCK_M - 1) / BLOCK_M), (int)((g.n + BLOCK_N - 1) / BLOCK_N));
   int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, THREADS, SMEM_BYTES, stream>>>(map_a, map_b, (float *)g.c, g.ldc, (int)g.m, (int)g.n, (int)g.k,
-                                              (float)g.alpha_re, (float)g.beta_re);
+                                              (float)g.alpha_re, (float)g.beta_re, g.tri);
   return cudaGetLastError();
 }
 
@@ -568,7 +585,7 @@ cudaError_t launch_2cta_variant(const DeviceGemm &g, cudaStream_t stream) {
   ok = ok && (B_MN ? make_map(&map_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, 64, BLOCK_K)
                    : make_map(&map_b, g.b, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.ldb, BLOCK_K, 128));
   if (!ok) return cudaErrorNotSupported;
-  int tiles = (int)(((g.m + two::TILE_M - 1) / two::TILE_M) * ((g.n + two::TILE_N - 1) / two::TILE_N));
+  int tiles = tile_count_for<false>(g.tri, (int)((g.m + two::TILE_M - 1) / two::TILE_M), (int)((g.n + two::TILE_N - 1) / two::TILE_N));
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
@@ -581,7 +598,7 @@ cudaError_t launch_2cta_variant(const DeviceGemm &g, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, (float *)g.c, g.ldc, (int)g.m, (int)g.n, (int)g.k,
-                            (float)g.alpha_re, (float)g.beta_re);
+                            (float)g.alpha_re, (float)g.beta_re, (int)g.tri);
 }
 
 }  // namespace
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(256) repack_bf16_kernel(int64_t rows, int64_t 
 
 cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g_in, cudaStream_t stream) {
   DeviceGemm g = g_in;
-  if (g.dtype != B200_SB || g.tri) return cudaErrorNotSupported;
+  if (g.dtype != B200_SB || (g.tri && g.m != g.n)) return cudaErrorNotSupported;
   if ((uintptr_t)g.c & 3) return cudaErrorNotSupported;
   if (g.m < 1 || g.n < 1 || g.k < 1) return cudaErrorNotSupported;
   if (g.m > (1 << 30) || g.n > (1 << 30) || g.k > (1 << 30)) return cudaErrorNotSupported;

@@ -96,6 +96,11 @@ class Oracle:
                                     C.c_void_p, C.c_long, C.c_void_p]
         L.oracle_sbdot.restype = C.c_double
         L.oracle_sbdot.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_sbgemmt.restype = C.c_int
+        L.oracle_sbgemmt.argtypes = [C.c_int] * 3 + [C.c_long, C.c_long, C.c_float, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_float,
+                                                     C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_check_sbgemmt.restype = C.c_int
+        L.oracle_check_sbgemmt.argtypes = [C.c_int] * 4 + [C.c_long] * 5 + [C.c_int]
         L.oracle_check_sbgemv.restype = C.c_int
         L.oracle_check_sbgemv.argtypes = [C.c_int] + [C.c_long] * 5 + [C.c_int]
 
@@ -182,6 +187,15 @@ class Oracle:
     def sbdot(self, n, x, incx, y, incy):
         g = C.c_double(0.0)
         return self.lib.oracle_sbdot(n, _ptr(x), incx, _ptr(y), incy, C.byref(g)), g.value
+
+    def sbgemmt(self, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """SBGEMMT in place on the uplo triangle of the fp32 c (a, b: uint16 bf16 arrays); returns the m x m gauge."""
+        g = np.zeros((max(m, 1), max(m, 1)), dtype=np.float64)
+        assert self.lib.oracle_sbgemmt(uplo, ta, tb, m, k, alpha, _ptr(a), lda, _ptr(b), ldb, beta, _ptr(c), ldc, _ptr(g)) == 0
+        return g
+
+    def check_sbgemmt(self, rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, ok):
+        return self.lib.oracle_check_sbgemmt(rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, ok)
 
     def check_sbgemv(self, trans, m, n, lda, incx, incy, ok):
         return self.lib.oracle_check_sbgemv(trans, m, n, lda, incx, incy, ok)
@@ -288,6 +302,19 @@ def call_gemmt(lib, dtype, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c, l
     i = lambda v: C.byref(C.c_int(int(v)))
     fn(C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(TRANS_CHAR[ta].encode()), C.c_char_p(TRANS_CHAR[tb].encode()), i(m), i(k),
        _ptr(al), P(a), i(lda), P(b), i(ldb), _ptr(be), P(c), i(ldc))
+    return c
+
+
+def call_sbgemmt(lib, uplo, ta, tb, m, k, alpha, a, lda, b, ldb, beta, c, ldc, cblas=False, rowmajor=False):
+    """sbgemmt_ or cblas_sbgemmt (interface/sbgemmt.c:47-52,143-149; neither is declared in cblas.h) of any library."""
+    P = lambda v: C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+    if cblas:
+        lib.cblas_sbgemmt(101 if rowmajor else 102, 121 if uplo == 0 else 122, CBLAS_TRANS[ta], CBLAS_TRANS[tb], C.c_int(m), C.c_int(k),
+                          C.c_float(alpha), P(a), C.c_int(lda), P(b), C.c_int(ldb), C.c_float(beta), P(c), C.c_int(ldc))
+        return c
+    i = lambda v: C.byref(C.c_int(int(v)))
+    lib.sbgemmt_(C.c_char_p(b"UL"[uplo:uplo + 1]), C.c_char_p(TRANS_CHAR[ta].encode()), C.c_char_p(TRANS_CHAR[tb].encode()), i(m), i(k),
+                 C.byref(C.c_float(alpha)), P(a), i(lda), P(b), i(ldb), C.byref(C.c_float(beta)), P(c), i(ldc))
     return c
 
 

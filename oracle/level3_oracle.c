@@ -467,6 +467,43 @@ double oracle_sbdot(long n, const unsigned short *x, long incx, const unsigned s
 }
 
 /* interface/sbgemv.c:86-92 / 130-135 (after the row-major swap of m, n and trans) */
+/* ---- SBGEMMT: the uplo triangle of the m x m fp32 matrix  C := alpha * op(A) * op(B) + beta * C,  A and B bf16 ----
+ * interface/sbgemmt.c:346-445 walks the triangle column by column and hands each column to the SBGEMV KERNEL
+ * (not the interface): kernel/x86_64/sbgemv_n.c:114 / sbgemv_t.c return at once when a dimension is < 1, so
+ * k == 0 leaves C untouched whatever beta is, and there is no alpha == 0 shortcut -- every element is
+ * alpha * acc (beta == 0, C not read) or alpha * acc + beta * C with one fp32 accumulator walked over k in order
+ * (sbgemv_n.c:63-72).  R / C fold to N / T (:90-104).  PINNED against oracle/_ref/generic (sbgemmt_, cblas_sbgemmt) in
+ * tests/test_f_rows_pin.py: bit for bit while a column stays on one thread, by bound otherwise. */
+int oracle_sbgemmt(int uplo, int transa, int transb, long m, long k, float alpha, const unsigned short *a, long lda,
+                   const unsigned short *b, long ldb, float beta, float *c, long ldc, double *gauge) {
+  if (gauge) for (long x = 0; x < m * m; x++) gauge[x] = 0;
+  if (m <= 0 || k <= 0) return 0;
+  transa &= 1; transb &= 1;
+  for (long j = 0; j < m; j++)
+    for (long i = uplo ? j : 0; i < (uplo ? m : j + 1); i++) {
+      float acc = 0.0f;
+      double g = 0;
+      for (long l = 0; l < k; l++) {
+        float av = bf16_widen(transa ? a[l + i * lda] : a[i + l * lda]), bv = bf16_widen(transb ? b[j + l * ldb] : b[l + j * ldb]);
+        acc += av * bv;
+        g += fabs((double)av) * fabs((double)bv);
+      }
+      g *= fabs((double)alpha);
+      float *y = c + i + j * ldc;
+      if (beta == 0.0f) *y = alpha * acc;
+      else { g += fabs((double)beta) * fabs((double)*y); *y = alpha * acc + beta * *y; }
+      if (gauge) gauge[i + j * m] = g;
+    }
+  return 0;
+}
+
+/* interface/sbgemmt.c:121-137 (column-major, both ABIs) and :286-301 (row-major: the checks run on the swapped
+ * problem and report the swapped positions, as in gemmt.c); unlike gemmt.c:322-323 the row-major branch does NOT
+ * flip uplo (:239-240), so a row-major call updates the OTHER triangle of the caller's C -- reproduced as is. */
+int oracle_check_sbgemmt(int rowmajor, int uplo, int transa, int transb, long m, long k, long lda, long ldb, long ldc, int ok) {
+  return oracle_check_gemmt(rowmajor, uplo, transa, transb, m, k, lda, ldb, ldc, ok);
+}
+
 int oracle_check_sbgemv(int trans, long m, long n, long lda, long incx, long incy, int ok) {
   int info = ok;
   if (incy == 0) info = 11;

@@ -149,7 +149,7 @@ cudaError_t launch_cgemm_ffma(const DeviceGemm &g, cudaStream_t) {
 }
 cudaError_t launch_sbgemm_tcgen05(const DeviceGemm &g, cudaStream_t) {
   /* the real launcher takes every shape and alignment (misaligned operands are repacked on the device first) */
-  if (g.dtype != B200_SB || g.tri || ((uintptr_t)g.c & 3) || g.m < 1 || g.n < 1 || g.k < 1) return cudaErrorNotSupported;
+  if (g.dtype != B200_SB || (g.tri && g.m != g.n) || ((uintptr_t)g.c & 3) || g.m < 1 || g.n < 1 || g.k < 1) return cudaErrorNotSupported;
   return sim_gemm(g, "sim_sbgemm");
 }
 

@@ -175,3 +175,28 @@ def test_random_argument_probes_of_gemmt_and_sbgemv_match_the_reference(tmp_path
             a = subprocess.run([str(exe), "30000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
             b = subprocess.run([str(ref), "30000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
             assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout
+
+
+def test_random_argument_probes_of_sbgemmt_match_the_reference(tmp_path, ob):
+    """tests/c/errexit_fuzz3.c: 2000 fixed-seed random calls of sbgemmt_ / cblas_sbgemmt (both orders and illegal
+    ones) must print, byte for byte, what the same program printed against the reference
+    (tests/golden/errexit_fuzz3_reference.txt, written from oracle/_ref/generic): routine name and length handed to
+    xerbla_ ("SBGEMMT ", 9), info -- the row-major branch reports the swapped positions -- and nothing for legal
+    calls.  Live with other seeds when the reference is present (100 000 calls compared when the fixture was made)."""
+    from oracle import cpu
+    src = os.path.join(ROOT, "tests", "c", "errexit_fuzz3.c")
+    exe = tmp_path / "errexit_fuzz3"
+    subprocess.check_call(["gcc", "-O1", "-Wall", f"-I{ROOT}/include", src, "-o", str(exe), f"-L{LIBDIR}", "-lopenblas_b200", f"-Wl,-rpath,{LIBDIR}"])
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    want = open(os.path.join(ROOT, "tests", "golden", "errexit_fuzz3_reference.txt")).read()
+    assert len(want.splitlines()) == 2001 and want.endswith("C untouched\n")
+    assert r.stdout == want, [(g, e) for g, e in zip(r.stdout.splitlines(), want.splitlines()) if g != e][:5]
+    if cpu.have_reference("generic"):
+        refdir = os.path.dirname(cpu.ref_path("generic"))
+        ref = tmp_path / "fz3_ref"
+        subprocess.check_call(["gcc", "-O1", f"-I{ROOT}/include", src, "-o", str(ref), f"-L{refdir}", "-lopenblas_ref", f"-Wl,-rpath,{refdir}"])
+        for seed in ("31", "32"):
+            a = subprocess.run([str(exe), "20000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
+            b = subprocess.run([str(ref), "20000", seed], stdout=subprocess.PIPE, text=True, timeout=300)
+            assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout
