@@ -141,5 +141,5 @@ def test_error_exits_print_the_reference_message(ob, oracle, capfd):
                               C.c_float(0.0), p, C.c_int(ldc))
             C.CDLL(None).fflush(None)
             out = "".join(capfd.readouterr())
-            assert f"SBGEMMT parameter number {want:2d}" in out, (rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, want, out)
+            assert f"SBGEMMT  parameter number {want:2d}" in out, (rowmajor, uplo, ta, tb, m, k, lda, ldb, ldc, want, out)
     assert probes >= 18 and (buf == 7.0).all()
