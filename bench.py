@@ -774,7 +774,10 @@ def run_sweep_level3(args):
             if cplx:
                 jobs += [("hemm", lambda: getattr(lib, dtype + "hemm_")(C.c_char_p(b"R"), C.c_char_p(b"L"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
                          ("herk", lambda: getattr(lib, dtype + "herk_")(C.c_char_p(b"U"), C.c_char_p(b"C"), i_(n), i_(k), C.byref(alr), pa, i_(n), C.byref(ber), pc, i_(n)), 1.0)]
+            want = [r for r in args.sweep_routines.split(",") if r]
             for name, f, factor in jobs:
+                if want and not any(name.startswith(r) for r in want):
+                    continue
                 f(); torch.cuda.synchronize()
                 reps = 3
                 t0 = time.perf_counter()                      # the BLAS call is synchronous: wall time of the call itself
@@ -809,6 +812,7 @@ def main():
     ap.add_argument("--sweep", action="store_true"); ap.add_argument("--sizes", default="1024,2048,4096,8192,16384")
     ap.add_argument("--sweep-level3", action="store_true", help="developer view: SYMM/SYRK/SYR2K/HEMM/HERK on device operands")
     ap.add_argument("--sweep-dtypes", default="d,s,z,c,sb")
+    ap.add_argument("--sweep-routines", default="", help="--sweep-level3: only routines whose name starts with one of these (comma separated)")
     ap.add_argument("--all-ops", action="store_true", help="sweep: all four N/T combinations at every size")
     args = ap.parse_args()
     if args.impl == "reference":
