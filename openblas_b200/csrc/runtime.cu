@@ -94,10 +94,6 @@ struct Context {
   size_t in_slot_bytes = 0, out_slot_bytes = 0;   /* grown on demand up to B200_SLOT_BYTES: a 1024^3 call pins 3 x 8 MB, not 6 x 32 MB */
   cudaEvent_t in_ev[kSlots] = {nullptr, nullptr, nullptr}, out_ev[kSlots] = {nullptr, nullptr, nullptr};
   cudaEvent_t order_ev = nullptr;                 /* orders the compute stream after the caller's legacy-stream work */
-  /* TRMM / TRSM: the lower levels of the recursion run as independent slices of B on these streams (tri_lanes) */
-  static const int kLanes = 3;
-  cudaStream_t lane[kLanes] = {nullptr, nullptr, nullptr};
-  cudaEvent_t lane_fork = nullptr, lane_join[kLanes] = {nullptr, nullptr, nullptr};
   bool in_busy[kSlots] = {false, false, false};
   int in_next = 0, out_next = 0;
   struct PendingOut { bool active = false; char *host; size_t hpitch, width, cols; };
@@ -173,7 +169,6 @@ static int acquire(ContextLease *lease) {
 }
 static void scrub(Context *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < Context::kLanes; i++) if (c->lane[i]) cudaStreamSynchronize(c->lane[i]);
   if (c->s_in) cudaStreamSynchronize(c->s_in);
   if (c->s_out) cudaStreamSynchronize(c->s_out);
   cudaGetLastError();
@@ -1111,11 +1106,6 @@ static void shutdown_impl(void) {
     }
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->order_ev) cudaEventDestroy(c->order_ev);
-    if (c->lane_fork) cudaEventDestroy(c->lane_fork);
-    for (int i = 0; i < Context::kLanes; i++) {
-      if (c->lane_join[i]) cudaEventDestroy(c->lane_join[i]);
-      if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
-    }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);

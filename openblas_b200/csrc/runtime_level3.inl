@@ -41,15 +41,6 @@ static int64_t rankk_block(int64_t n) { return n >= 4096 ? 512 : n >= 1024 ? 256
  * B200_SYMM_PANEL_BYTES, i.e. ka / width GEMMs with inner dimension `width` accumulating into C -- a 65536^2 ZHEMM
  * then needs 0.5 GiB of workspace instead of 64 GiB (round 1 expanded in full, always). */
 #ifdef B200_HOSTSIM
-#define B200_TRI_LANE_BELOW_DEFAULT 256      /* hostsim: small enough for matrices a CPU test multiplies */
-#define B200_TRI_LANE_MIN 24
-#define B200_TRI_LANE_ALIGN 8
-#else
-#define B200_TRI_LANE_BELOW_DEFAULT 1024
-#define B200_TRI_LANE_MIN 1024
-#define B200_TRI_LANE_ALIGN 128
-#endif
-#ifdef B200_HOSTSIM
 #define B200_SYMM_FULL_BYTES  ((size_t)16 << 10)
 #define B200_SYMM_PANEL_BYTES ((size_t)8 << 10)
 #define B200_SYMM_PANEL_ALIGN 8
@@ -86,7 +77,6 @@ static size_t symm_scratch_bytes(int64_t ka, size_t es) {
 struct TriWork {
   int dtype, op; bool solve, left, eff_lower, unit;
   const char *a; int64_t lda; char *b; int64_t ldb; int64_t m, n; size_t es; cudaStream_t s;
-  Context *ctx = nullptr;       /* owner of the lane streams; nullptr inside a lane (no nested forks) */
   /* rows [r0, ..) x cols [c0, ..) of E as a GEMM operand that still needs `op` applied */
   const char *eblk(int64_t r0, int64_t c0) const { return a + ((op & 1) ? ((size_t)c0 + (size_t)r0 * lda) : ((size_t)r0 + (size_t)c0 * lda)) * es; }
   char *bpart(int64_t off) const { return b + (left ? (size_t)off : (size_t)off * ldb) * es; }   /* rows (left) or columns (right) from off */
@@ -100,61 +90,8 @@ static cudaError_t tri_gemm(const TriWork &w, int64_t r0, int64_t nr, int64_t c0
   return gemm_on_device(w.dtype, B200_N, w.op, w.m, nc, nr, ar, ai, w.bpart(r0), w.ldb, w.eblk(r0, c0), w.lda, br, bi, w.bpart(c0), w.ldb, w.s);
 }
 
-/* The lower levels of the recursion are chains of small kernels: a 128-row block solve is ONE wave of CTAs bound by the
- * latency of its 128 dependent steps, the GEMMs between them have 128 ... 512 rows and a short inner dimension, and each
- * must finish before the next starts (ncu launch list of a DTRSM 8192^2, profiles/r02_dtrsm8192_launches_*: the levels
- * <= 512 and the block solves take 4.6 of 19.2 ms for 1/8 of the flops).  The columns of B (side left; the rows for side
- * right) are independent problems, so below B200_TRI_LANE_BELOW rows the sub-triangle is solved as up to four slices of
- * B on four streams: the chains run side by side and one slice's GEMM fills the SMs another slice's solve leaves idle.
- * Fork / join are events on the calling stream; the large GEMMs above the threshold stay whole. */
-static int tri_lanes_wanted() {
-  static const int v = [] { const char *e = getenv("B200_TRI_LANES"); int n = e ? atoi(e) : 4; return n < 1 ? 1 : n > 1 + Context::kLanes ? 1 + Context::kLanes : n; }();
-  return v;
-}
-static int64_t tri_lane_below() {
-  static const int64_t v = [] { const char *e = getenv("B200_TRI_LANE_BELOW"); return e ? (int64_t)atol(e) : (int64_t)B200_TRI_LANE_BELOW_DEFAULT; }();
-  return v;
-}
-static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, double ai);
-static int tri_forked(const TriWork &w, int64_t off, int64_t size, double ar, double ai, int lanes) {
-  Context *c = w.ctx;
-  const int64_t free_dim = w.left ? w.n : w.m;
-  const int64_t slice = ((free_dim + lanes - 1) / lanes + B200_TRI_LANE_ALIGN - 1) / B200_TRI_LANE_ALIGN * B200_TRI_LANE_ALIGN;
-  if (!c->lane_fork) CK(cudaEventCreateWithFlags(&c->lane_fork, cudaEventDisableTiming));
-  CK(cudaEventRecord(c->lane_fork, w.s));
-  int used = 0, err;
-  for (int l = 0; l < lanes; l++) {
-    const int64_t x0 = (int64_t)l * slice, nx = free_dim - x0 < slice ? free_dim - x0 : slice;
-    if (nx <= 0) break;
-    TriWork v = w;
-    v.ctx = nullptr;
-    if (w.left) { v.b = w.b + (size_t)x0 * (size_t)w.ldb * w.es; v.n = nx; }
-    else        { v.b = w.b + (size_t)x0 * w.es; v.m = nx; }
-    if (l > 0) {
-      if (!c->lane[l - 1]) CK(cudaStreamCreateWithFlags(&c->lane[l - 1], cudaStreamNonBlocking));
-      if (!c->lane_join[l - 1]) CK(cudaEventCreateWithFlags(&c->lane_join[l - 1], cudaEventDisableTiming));
-      v.s = c->lane[l - 1];
-      CK(cudaStreamWaitEvent(v.s, c->lane_fork, 0));
-      used = l;
-    }
-    if ((err = tri_recurse(v, off, size, ar, ai))) return err;
-  }
-  for (int l = 1; l <= used; l++) {
-    CK(cudaEventRecord(c->lane_join[l - 1], c->lane[l - 1]));
-    CK(cudaStreamWaitEvent(w.s, c->lane_join[l - 1], 0));
-  }
-  return 0;
-}
-
 static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, double ai) {
   const int64_t base = tri_block_max(w.dtype);       /* 128 (real types) or 64 */
-  if (w.ctx && size <= tri_lane_below() && size > base) {
-    /* every slice keeps at least B200_TRI_LANE_MIN columns (rows): below that the slices' GEMMs are too thin to gain */
-    const int64_t free_dim = w.left ? w.n : w.m;
-    int lanes = tri_lanes_wanted();
-    while (lanes > 1 && free_dim / lanes < B200_TRI_LANE_MIN) lanes--;
-    if (lanes > 1) return tri_forked(w, off, size, ar, ai, lanes);
-  }
   if (size <= base) {
     const bool tr = (w.op & 1) != 0;
     /* left: E(i,k) = op(F)(i,k); right: the kernel works on E^T */
@@ -187,7 +124,7 @@ static int tri_recurse(const TriWork &w, int64_t off, int64_t size, double ar, d
 
 /* everything on the device, pointers are device pointers; scratch holds the expanded operand
  * (SYMM/HEMM) or one NB x NB tile (the others) */
-static int level3_on_device(Context *ctx, const b200_l3_problem *p, const char *a, int64_t lda, const char *b, int64_t ldb, char *c,
+static int level3_on_device(const b200_l3_problem *p, const char *a, int64_t lda, const char *b, int64_t ldb, char *c,
                             int64_t ldc, char *scratch, cudaStream_t s) {
   const size_t es = b200_in_size(p->dtype);
   const double ar = p->alpha[0], ai = p->alpha[1], br = p->beta[0], bi = p->beta[1];
@@ -232,7 +169,7 @@ static int level3_on_device(Context *ctx, const b200_l3_problem *p, const char *
     TriWork w;
     w.dtype = p->dtype; w.op = p->trans; w.solve = p->routine == B200_TRSM; w.left = !p->side;
     w.eff_lower = (p->uplo != 0) != ((p->trans & 1) != 0); w.unit = p->unit != 0;
-    w.a = a; w.lda = lda; w.b = c; w.ldb = ldc; w.m = p->m; w.n = p->n; w.es = es; w.s = s; w.ctx = ctx;
+    w.a = a; w.lda = lda; w.b = c; w.ldb = ldc; w.m = p->m; w.n = p->n; w.es = es; w.s = s;
     return tri_recurse(w, 0, p->side ? p->n : p->m, ar, ai);
   }
 
@@ -386,7 +323,7 @@ static int run_level3_on_context(Context *ctx, const b200_l3_problem *p) {
                          (size_t)o.cols))) return err;
     }
   }
-  if ((err = level3_on_device(ctx, p, A.dev, A.ld_dev, B.dev, B.ld_dev, C.dev, C.ld_dev, scratch, s))) return err;
+  if ((err = level3_on_device(p, A.dev, A.ld_dev, B.dev, B.ld_dev, C.dev, C.ld_dev, scratch, s))) return err;
   if (C.kind != PTR_DEVICE) {
     if (small) {
       const size_t c_off = (size_t)(C.dev - ctx->dws);

@@ -222,29 +222,6 @@ def test_trxm_recursion_offsets(sim, oracle, dtype):
                         L.check_trxm(oracle, sim, (dtype, solve, side, uplo, trans, unit, m, n, ka + 1, m + 2, alpha), a, b0)
 
 
-@pytest.mark.parametrize("dtype", [cpu.D, cpu.CX])
-def test_trxm_lower_levels_run_as_slices_of_b(sim, oracle, dtype):
-    """tri_forked (runtime_level3.inl): below the lane threshold (256 rows in this build) the sub-triangle is processed as
-    up to four slices of B's columns (side left) or rows (side right) on separate streams; ragged slices, a free
-    dimension too small to slice, and a triangle that forks only in its first half."""
-    rng = np.random.default_rng(950 + dtype)
-    cplx = dtype in (cpu.CX, cpu.Z)
-    alpha = (0.7 - 0.9j) if cplx else 0.7
-    for solve in (0, 1):
-        for side in (0, 1):
-            for uplo in (0, 1):
-                for trans in range(4 if cplx else 2):
-                    for ka, free in ((200, 101), (300, 64), (140, 30)):
-                        m, n = (free, ka) if side else (ka, free)
-                        unit = (trans + uplo) % 2
-                        a = L.tri_operand(rng, dtype, ka, ka + 3, uplo, unit)
-                        if solve:
-                            off = ~np.eye(ka, ka + 3, dtype=bool)
-                            a[off] *= 4.0 / ka
-                        b0 = L.operand(rng, dtype, n, m + 1)
-                        L.check_trxm(oracle, sim, (dtype, solve, side, uplo, trans, unit, m, n, ka + 3, m + 1, alpha), a, b0)
-
-
 def test_row_major_cblas_entry_points(sim):
     """Row-major normalisation of every family against numpy on the logical matrices."""
     rng = np.random.default_rng(5)
