@@ -300,13 +300,40 @@ B200_EXPORT int b200_summa_unique_id(void *id128) {
 B200_EXPORT int b200_summa_destroy(b200_summa *h);
 
 /* Collective over `world` processes, each bound to its own GPU (the current device of the calling thread). */
+static int summa_setup(b200_summa *h, const void *id128, int rank, int world);
+
+/* local release of a handle whose creation failed half way: no collective call (the peers may have failed elsewhere),
+ * so NCCL communicators that already exist are left to process exit */
+static void summa_abandon(b200_summa *h) {
+  close_window(h);
+  for (int r = 0; r < (int)h->peer_ctl.size(); r++)
+    if (r != h->rank && h->peer_ctl[(size_t)r]) cudaIpcCloseMemHandle(h->peer_ctl[(size_t)r]);
+  if (h->ctl) cudaFree(h->ctl);
+  if (h->flag) cudaFree(h->flag);
+  cudaEvent_t evs[] = {h->ev_cup, h->ev_entry, h->ev_packed, h->ev_exit, h->ev_a[0], h->ev_a[1], h->ev_b[0], h->ev_b[1], h->ev_free[0], h->ev_free[1],
+                       h->ev_strip[0], h->ev_strip[1]};
+  for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  cudaStream_t ss[] = {h->s_pack, h->s_a, h->s_b, h->s_out};
+  for (cudaStream_t st : ss) if (st) cudaStreamDestroy(st);
+  cudaGetLastError();
+  delete h;
+}
+
 B200_EXPORT int b200_summa_create(b200_summa **out, const void *id128, int rank, int world, int P, int Q) {
+  if (!out) return fail("b200_summa_create", "no place for the handle");
   *out = nullptr;
-  if (world < 1 || rank < 0 || rank >= world || P * Q != world || world > Control::kMaxRanks) return fail("b200_summa_create", "bad rank / world / grid");
+  if (world < 1 || rank < 0 || rank >= world || P < 1 || Q < 1 || P * Q != world || world > Control::kMaxRanks) return fail("b200_summa_create", "bad rank / world / grid");
+  if (world > 1 && !id128) return fail("b200_summa_create", "no unique id (b200_summa_unique_id on one rank, distributed to all)");
   b200_summa *h = new b200_summa();
   h->rank = rank; h->world = world; h->P = P; h->Q = Q; h->p = rank / Q; h->q = rank % Q;
+  if (summa_setup(h, id128, rank, world)) { summa_abandon(h); return 1; }   /* the thread's error text says what failed */
+  *out = h;
+  return 0;
+}
+
+static int summa_setup(b200_summa *h, const void *id128, int rank, int world) {
   CU(cudaGetDevice(&h->device));
-  if (b200_init(h->device) != 0) { delete h; return 1; }
+  if (b200_init(h->device) != 0) return 1;
   const char *tv = getenv("B200_SUMMA_TRANSPORT"), *sv = getenv("B200_SUMMA_SYNC");
   h->transport = (tv && !strcmp(tv, "nccl")) ? TRANSPORT_NCCL : TRANSPORT_PULL;
   h->sync = (sv && !strcmp(sv, "nccl")) ? SYNC_NCCL : SYNC_MEMOPS;
@@ -328,7 +355,7 @@ B200_EXPORT int b200_summa_create(b200_summa **out, const void *id128, int rank,
   h->peer_ctl[(size_t)rank] = h->ctl;
   h->peer_win.assign((size_t)world, nullptr);
   if (world > 1) {
-    if (!g_nccl.load()) { delete h; return fail("dlopen", "libnccl.so.2 not found (set B200_NCCL_LIB)"); }
+    if (!g_nccl.load()) return fail("dlopen", "libnccl.so.2 not found (set B200_NCCL_LIB)");
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
@@ -347,7 +374,6 @@ B200_EXPORT int b200_summa_create(b200_summa **out, const void *id128, int rank,
     if (nccl_barrier(h, h->s_pack)) return 1;
     CU(cudaStreamSynchronize(h->s_pack));
   }
-  *out = h;
   return 0;
 }
 
@@ -383,6 +409,7 @@ B200_EXPORT int b200_summa_destroy(b200_summa *h) {
 B200_EXPORT uint64_t b200_summa_launches(const b200_summa *h) { return h ? h->launches : 0; }
 B200_EXPORT const char *b200_summa_describe(const b200_summa *h) {
   static thread_local char buf[320];
+  if (!h) return "summa: no handle";
   snprintf(buf, sizeof buf, "summa %dx%d rank %d (p=%d,q=%d): panels by %s, synchronised by %s", h->P, h->Q, h->rank, h->p, h->q,
            h->transport == TRANSPORT_PULL ? "copy-engine pulls from peer windows (CUDA IPC over NVLink)" : "ncclBroadcast on row/column communicators",
            h->sync == SYNC_MEMOPS ? "stream memory operations on peer control blocks" : "NCCL");

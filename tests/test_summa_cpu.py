@@ -133,3 +133,26 @@ def test_c_driver_layout_functions_agree_with_the_python_mirror():
         cnt = L.b200_summa_schedule(k, nb, P, Q, cap, k0, w, ao, al, bo, bl)
         assert cnt == len(steps)
         assert [(k0[i], w[i], ao[i], al[i], bo[i], bl[i]) for i in range(cnt)] == steps
+
+
+def test_c_driver_rejects_bad_handles_and_grids_before_touching_cuda():
+    """b200_summa_create / b200_summa_gemm / b200_summa_describe with arguments that can never work: an error code and
+    the reason in b200_last_error, no handle, no CUDA call (this runs without a GPU)."""
+    import ctypes as C
+    import openblas_b200 as ob
+    L = ob.lib()
+    L.b200_summa_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200_summa_describe.restype = C.c_char_p
+    L.b200_summa_describe.argtypes = [C.c_void_p]
+    L.b200_summa_destroy.argtypes = [C.c_void_p]
+    L.b200_last_error.restype = C.c_char_p
+    ident = bytes(128)
+    for rank, world, P, Q in ((0, 4, 2, 3), (4, 4, 2, 2), (-1, 2, 1, 2), (0, 0, 0, 0), (0, 128, 8, 16), (0, 2, -1, -2)):
+        h = C.c_void_p(0x1234)
+        assert L.b200_summa_create(C.byref(h), ident, rank, world, P, Q) != 0
+        assert h.value is None and b"bad rank / world / grid" in L.b200_last_error()
+    h = C.c_void_p(0x1234)
+    assert L.b200_summa_create(C.byref(h), None, 0, 2, 1, 2) != 0 and h.value is None and b"unique id" in L.b200_last_error()
+    assert L.b200_summa_create(None, ident, 0, 1, 1, 1) != 0
+    assert L.b200_summa_destroy(None) == 0
+    assert b"no handle" in L.b200_summa_describe(None)
