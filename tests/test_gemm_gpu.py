@@ -297,6 +297,17 @@ def test_bf16_helpers_match_reference_vectors(ob):
     h2 = np.full(2 * 50, 0xdead, dtype=np.uint16)
     ob.lib().cblas_sbstobf16(50, x.ctypes.data, 1, h2.ctypes.data, -2)
     assert np.array_equal(h2[::2][::-1], g["bf16"][:50]) and np.all(h2[1::2] == 0xdead)
+    # one element per call, the way test/compare_sgemm_sbgemm.c converts its matrices (the in-place pinned path), all four directions
+    import ctypes as C
+    L = ob.lib()
+    for i in range(0, x.size, max(1, x.size // 64)):
+        one, one_back, d_in, d_out, d_back = np.zeros(1, np.uint16), np.zeros(1, np.float32), x[i:i + 1].astype(np.float64), np.zeros(1, np.uint16), np.zeros(1, np.float64)
+        L.cblas_sbstobf16(1, C.c_void_p(x[i:i + 1].ctypes.data), 1, C.c_void_p(one.ctypes.data), 1)
+        L.cblas_sbf16tos(1, C.c_void_p(one.ctypes.data), 1, C.c_void_p(one_back.ctypes.data), 1)
+        L.cblas_sbdtobf16(1, C.c_void_p(d_in.ctypes.data), 1, C.c_void_p(d_out.ctypes.data), 1)
+        L.cblas_dbf16tod(1, C.c_void_p(d_out.ctypes.data), 1, C.c_void_p(d_back.ctypes.data), 1)
+        assert one[0] == g["bf16"][i] and one_back.view(np.uint32)[0] == g["back"].view(np.uint32)[i]
+        assert d_out[0] == g["bf16"][i] and np.float32(d_back[0]).view(np.uint32) == g["back"].view(np.uint32)[i]
 
 
 def test_concurrent_callers_get_identical_results(ob, oracle):
@@ -354,9 +365,14 @@ def test_tile_aligned_shapes_take_the_roofline_kernels(ob, oracle, dtype):
     import torch
     rng = np.random.default_rng(5000 + dtype)
     shapes = [(256, 512, 256), (384, 768, 416)]     # kept small: the CPU oracle is O(mnk) scalar code
-    for (m, n, k) in shapes:
+    cplx = dtype in (cpu.CX, cpu.Z)
+    if cplx:                                         # complex tiles are half as wide: the same tile counts at half the extents
+        shapes = [(128, 256, 256), (256, 384, 416)]
+    for si, (m, n, k) in enumerate(shapes):
         for ta in range(ntrans(dtype)):
             for tb in range(ntrans(dtype)):
+                if cplx and si == 1 and (tb - ta) % 4 != 1:
+                    continue                         # the larger complex shape: a Latin quarter of the 16 op pairs (every op of A and of B once)
                 a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(8, 16, 24))
                 alpha, beta = alpha_beta(dtype)[0][2], alpha_beta(dtype)[1][2]
                 view = {np.uint16: np.int16}.get(a.dtype.type, a.dtype.type)

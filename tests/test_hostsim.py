@@ -273,6 +273,15 @@ def test_bf16_conversions_through_the_host_path(sim):
     h2 = np.full(2 * 50, 0xdead, dtype=np.uint16)
     sim.cblas_sbstobf16(50, x.ctypes.data_as(C.c_void_p), 1, h2.ctypes.data_as(C.c_void_p), -2)
     assert np.array_equal(h2[::2][::-1], g["bf16"][:50]) and np.all(h2[1::2] == 0xdead)
+    # one element per call (the in-place pinned path of run_convert_on_context), all four directions
+    for i in range(0, x.size, max(1, x.size // 64)):
+        one, one_back, d_in, d_out, d_back = np.zeros(1, np.uint16), np.zeros(1, np.float32), x[i:i + 1].astype(np.float64), np.zeros(1, np.uint16), np.zeros(1, np.float64)
+        sim.cblas_sbstobf16(1, C.c_void_p(x[i:i + 1].ctypes.data), 1, C.c_void_p(one.ctypes.data), 1)
+        sim.cblas_sbf16tos(1, C.c_void_p(one.ctypes.data), 1, C.c_void_p(one_back.ctypes.data), 1)
+        sim.cblas_sbdtobf16(1, C.c_void_p(d_in.ctypes.data), 1, C.c_void_p(d_out.ctypes.data), 1)
+        sim.cblas_dbf16tod(1, C.c_void_p(d_out.ctypes.data), 1, C.c_void_p(d_back.ctypes.data), 1)
+        assert one[0] == g["bf16"][i] and one_back.view(np.uint32)[0] == g["back"].view(np.uint32)[i]
+        assert d_out[0] == g["bf16"][i] and np.float32(d_back[0]).view(np.uint32) == g["back"].view(np.uint32)[i]
 
 
 def _build_and_run_thread_test(sanitize):
