@@ -666,6 +666,15 @@ def run_extras(ob, torch, dev, stream, args):
         r, kern, w = one("sb", NT4 if size == 4096 else [(0, 0)], size, size, size, 20 if size <= 4096 else 5, check=size <= 4096)
         sbs[f"sbgemm_{size}"] = {"tflops": r, "frac_of_burst_peak": r["NN"] / pb, "kernel": kern}
     out["sbgemm_sweep"] = sbs
+    # (e) SURVEY 8 f3: the rest of level 3 at 8192 (timing only; parity is the -m gpu tests' job), and SBGEMMT
+    torch.cuda.empty_cache()
+    fam = {}
+    for row in level3_rows(torch, ob, dev, ["d", "s", "z", "c"], [8192], []):
+        fam[row["routine"]] = {"ms": row["ms"], "tflops_useful": row["tflops_useful"], "frac_of_gemm_peak": row["frac_of_gemm_peak"],
+                               "launches_per_call": row["launches_per_call"]}
+    fam["sbgemmt"] = sbgemmt_row(torch, ob, dev, 8192)
+    fam["note"] = "n = k = 8192, device-resident operands, wall time of the synchronous Fortran-ABI calls (3 after a warm-up); flops as a GEMM of the same useful work"
+    out["level3_8192"] = fam
     return out
 
 
@@ -744,20 +753,27 @@ def run_sweep_level3(args):
     """Developer view: the symmetric level-3 family on device-resident operands, TFLOP/s with the
     conventional flop counts (SYMM 2*m*m*n, SYRK n*n*k, SYR2K 2*n*n*k, TRMM/TRSM m*m*n real; complex x4) -- what a GEMM
     of the same useful work would be credited with."""
-    import ctypes as C
     import torch
     import openblas_b200 as ob
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    return level3_rows(torch, ob, dev, [d for d in args.sweep_dtypes.split(",") if d in "sdcz"], [int(x) for x in args.sizes.split(",")],
+                       [r for r in args.sweep_routines.split(",") if r], echo=True)
+
+
+def level3_rows(torch, ob, dev, dtypes, sizes, want, echo=False):
+    """SURVEY 8 f3 routines through their Fortran entry points on device-resident n x n operands: wall time of the
+    (synchronous) calls, 3 after one warm-up; one row per routine."""
+    import ctypes as C
     lib = ob.lib()
     rows = []
     i_ = lambda v: C.byref(C.c_int(int(v)))
-    for dtype in [d for d in args.sweep_dtypes.split(",") if d in "sdcz"]:
+    for dtype in dtypes:
         cplx = dtype in "cz"
         rdt = torch.float64 if dtype in "dz" else torch.float32
         ct = C.c_double if dtype in "dz" else C.c_float
         peak, _ = measured_peak(dtype)
-        for nsz in [int(x) for x in args.sizes.split(",")]:
+        for nsz in sizes:
             n = k = nsz
             mk = lambda: (torch.rand((nsz, nsz, 2) if cplx else (nsz, nsz), device=dev, dtype=rdt) - 0.5)
             a, b, c = mk(), mk(), mk()
@@ -774,7 +790,6 @@ def run_sweep_level3(args):
             if cplx:
                 jobs += [("hemm", lambda: getattr(lib, dtype + "hemm_")(C.c_char_p(b"R"), C.c_char_p(b"L"), i_(n), i_(n), al2, pa, i_(n), pb, i_(n), be2, pc, i_(n)), 2.0),
                          ("herk", lambda: getattr(lib, dtype + "herk_")(C.c_char_p(b"U"), C.c_char_p(b"C"), i_(n), i_(k), C.byref(alr), pa, i_(n), C.byref(ber), pc, i_(n)), 1.0)]
-            want = [r for r in args.sweep_routines.split(",") if r]
             for name, f, factor in jobs:
                 if want and not any(name.startswith(r) for r in want):
                     continue
@@ -788,9 +803,33 @@ def run_sweep_level3(args):
                 rows.append({"routine": dtype + name, "n": nsz, "k": nsz, "ms": ms, "tflops_useful": tf, "frac_of_gemm_peak": tf / peak,
                              "launches_per_call": None})
                 l0 = ob.cblas.launch_count(); f(); rows[-1]["launches_per_call"] = int(ob.cblas.launch_count() - l0)
-                print(json.dumps(rows[-1]), flush=True)
+                if echo:
+                    print(json.dumps(rows[-1]), flush=True)
             del a, b, c
     return rows
+
+
+def sbgemmt_row(torch, ob, dev, n):
+    """SBGEMMT (sbgemmt_, lower triangle, NN) on device-resident bf16 operands: the triangle's n (n + 1) k flops per second."""
+    import ctypes as C
+    lib = ob.lib()
+    i_ = lambda v: C.byref(C.c_int(int(v)))
+    a = (torch.rand((n, n), device=dev) - 0.5).to(torch.bfloat16)
+    b = (torch.rand((n, n), device=dev) - 0.5).to(torch.bfloat16)
+    c = torch.zeros((n, n), device=dev, dtype=torch.float32)
+    al, be = C.c_float(1.0), C.c_float(0.0)
+    f = lambda: lib.sbgemmt_(C.c_char_p(b"L"), C.c_char_p(b"N"), C.c_char_p(b"N"), i_(n), i_(n), C.byref(al), C.c_void_p(a.data_ptr()), i_(n),
+                             C.c_void_p(b.data_ptr()), i_(n), C.byref(be), C.c_void_p(c.data_ptr()), i_(n))
+    f(); torch.cuda.synchronize()
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        f()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    # element (i, j) of the column-major C is c[j, i]: the strict upper triangle (i < j) must still be zero
+    untouched = bool((torch.tril(c, diagonal=-1) == 0).all().item())
+    return {"routine": "sbgemmt", "n": n, "k": n, "ms": ms, "tflops_triangle": n * (n + 1.0) * n / (ms * 1e-3) / 1e12, "kernel": ob.cblas.last_kernel(),
+            "other_triangle_untouched": untouched}
 
 
 def main():
