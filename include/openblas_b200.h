@@ -274,7 +274,9 @@ void zgemmt_(char *UPLO, char *TRANSA, char *TRANSB, blasint *M, blasint *K, dou
 /* ---- SBGEMMT: ?GEMMT with bf16 A and B, fp32 alpha, beta and C (interface/sbgemmt.c:47-52 Fortran,
  *      :143-149 CBLAS; built under BUILD_BFLOAT16, interface/Makefile:52,290,1306,1970; the reference declares it in
  *      no public header).  One triangle-masked launch of the tcgen05 SBGEMM kernel.  As in the reference: K == 0
- *      leaves C untouched whatever beta is, and a RowMajor call does NOT flip Uplo (sbgemmt.c:239-240). */
+ *      leaves C untouched whatever beta is, and a RowMajor call does NOT flip Uplo (sbgemmt.c:239-240).  One
+ *      deviation: with alpha == 0 the reference still forms 0 * (A B) in its SBGEMV kernels, so NaN / Inf in A or B
+ *      reach C; here alpha == 0 follows the BLAS convention (A and B are not read, the triangle is scaled by beta). */
 void cblas_sbgemmt(enum CBLAS_ORDER Order, enum CBLAS_UPLO Uplo, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
                    blasint M, blasint K, float alpha, const bfloat16 *A, blasint lda, const bfloat16 *B, blasint ldb,
                    float beta, float *C, blasint ldc);
