@@ -97,6 +97,18 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { *e = (cudaE
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 
+/* what csrc/summa.cu needs beyond the above; a 1 x 1 grid never talks to a peer, so the IPC and driver entry points only
+ * have to exist (they answer "not supported": the driver then takes its NCCL-synchronised branch, unused at world == 1) */
+cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {
+  *fn = nullptr;
+  if (q) *q = cudaDriverEntryPointSymbolNotFound;
+  return cudaSuccess;
+}
+
 /* hooks for the tests */
 __attribute__((visibility("default"))) void *hostsim_device_alloc(size_t n) { return alloc_block(n, 1); }
 __attribute__((visibility("default"))) void *hostsim_pinned_alloc(size_t n) { return alloc_block(n, 2); }

@@ -653,3 +653,78 @@ def test_sbgemv_sbdot_on_device_operands_use_the_callers_increments(sim, oracle)
     dx = sim.hostsim_device_alloc(x.nbytes); C.memmove(dx, x.ctypes.data, x.nbytes)
     assert np.float32(cpu.call_sbdot(sim, 25, dx, 2, x, -1)) == np.float32(oracle.sbdot(25, x, 2, x, -1)[0])
     sim.hostsim_free(dx)
+
+
+# ---------------------------------------------------------------- the SUMMA driver's host logic on a 1 x 1 grid
+os.environ.setdefault("B200_SUMMA_HOST_HALVES", "64")     # read once by the driver: local C of >= 64 columns is swept in two halves
+
+
+@pytest.mark.parametrize("dtype", [cpu.D, cpu.S, cpu.Z, cpu.CX])
+def test_summa_c_driver_on_a_1x1_grid_over_the_stand_in(sim, oracle, dtype):
+    """csrc/summa.cu compiled into the stand-in build: window packing (A dense, B panel-major), the k-panel schedule with
+    ragged last panels, host and "device" operands, a host C swept in one pass or in two column halves, beta == 0 over a
+    NaN C, k == 0, empty local pieces -- against the oracle (each panel is one simulated launch with beta = 1 after the
+    first, so the comparison is by the k * eps bound).  Peers, flags and IPC are the multi-GPU runs' business."""
+    L = sim
+    L.b200_summa_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200_summa_destroy.argtypes = [C.c_void_p]
+    L.b200_summa_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.b200_summa_launches.restype = C.c_uint64
+    L.b200_summa_launches.argtypes = [C.c_void_p]
+    L.b200_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    assert L.b200_summa_create(C.byref(h), None, 0, 1, 1, 1) == 0, L.b200_last_error()
+    rng = np.random.default_rng(600 + dtype)
+    cplx = dtype in (cpu.CX, cpu.Z)
+    t = cpu.NP_OUT[dtype]
+    try:
+        for (m, n, k, nb) in ((130, 90, 70, 32), (40, 200, 33, 16), (64, 64, 64, 64), (50, 40, 0, 8), (33, 17, 5, 64), (0, 9, 4, 4), (7, 0, 4, 4)):
+            for where in ("host", "device"):
+                for alpha, beta in (((0.7 - 0.9j, 1.3 - 1.1j) if cplx else (0.7, 1.3)), (1.0, 0.0)):
+                    lda, ldb, ldc = max(m, 1) + 3, max(k, 1) + 2, max(m, 1) + 1
+                    a, b, c0 = L_operand(rng, t, cplx, max(k, 1), lda), L_operand(rng, t, cplx, max(n, 1), ldb), L_operand(rng, t, cplx, max(n, 1), ldc)
+                    want = c0.copy()
+                    if m > 0 and n > 0:
+                        oracle.gemm(dtype, 0, 0, m, n, k, alpha, a, lda, b, ldb, beta, want, ldc)
+                    start = c0.copy()
+                    if beta == 0.0 and m > 0 and n > 0:
+                        start[:n, :m] = np.nan                       # beta == 0 never reads C
+                    al, be = cpu.scalar_bytes(dtype, alpha), cpu.scalar_bytes(dtype, beta)
+                    before = L.b200_summa_launches(h)
+                    if where == "host":
+                        got = start.copy()
+                        rc = L.b200_summa_gemm(h, dtype, m, n, k, nb, al.ctypes.data, a.ctypes.data, lda, b.ctypes.data, ldb, be.ctypes.data, got.ctypes.data, ldc, None)
+                    else:
+                        bufs = []
+                        for arr in (a, b, start):
+                            p = sim.hostsim_device_alloc(arr.nbytes)
+                            C.memmove(p, arr.ctypes.data, arr.nbytes)
+                            bufs.append(p)
+                        rc = L.b200_summa_gemm(h, dtype, m, n, k, nb, al.ctypes.data, bufs[0], lda, bufs[1], ldb, be.ctypes.data, bufs[2], ldc, None)
+                        got = np.empty_like(start)
+                        C.memmove(got.ctypes.data, bufs[2], start.nbytes)
+                        for p in bufs:
+                            sim.hostsim_free(p)
+                    assert rc == 0, L.b200_last_error()
+                    if m > 0 and n > 0:
+                        steps = (k + nb - 1) // nb if k > 0 else 1
+                        sweeps = 2 if (where == "host" and n >= 64 and steps >= 2) else 1
+                        assert L.b200_summa_launches(h) - before == steps * sweeps, (m, n, k, nb, where)
+                        ratio = oracle.ratio(dtype, 0, 0, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, got, ldc, want, ldc)
+                        assert ratio <= 2.0, (m, n, k, nb, where, alpha, ratio)
+                    # rows beyond m (and everything when the local piece is empty) keep their bytes
+                    pad = np.ones(start.shape, dtype=bool)
+                    if m > 0 and n > 0:
+                        pad[:n, :m] = False
+                    assert np.array_equal(got.view(np.uint8)[np.repeat(pad, got.itemsize, axis=1)], start.view(np.uint8)[np.repeat(pad, got.itemsize, axis=1)]), \
+                        (m, n, k, nb, where, "bytes outside the local piece changed")
+    finally:
+        assert L.b200_summa_destroy(h) == 0
+
+
+def L_operand(rng, t, cplx, cols, ld):
+    x = rng.random((cols, ld)) - 0.5
+    if cplx:
+        x = x + 1j * (rng.random((cols, ld)) - 0.5)
+    return x.astype(t)
