@@ -656,15 +656,15 @@ def test_sbgemv_sbdot_on_device_operands_use_the_callers_increments(sim, oracle)
 
 
 # ---------------------------------------------------------------- the SUMMA driver's host logic on a 1 x 1 grid
-os.environ.setdefault("B200_SUMMA_HOST_HALVES", "64")     # read once by the driver: local C of >= 64 columns is swept in two halves
-
-
 @pytest.mark.parametrize("dtype", [cpu.D, cpu.S, cpu.Z, cpu.CX])
-def test_summa_c_driver_on_a_1x1_grid_over_the_stand_in(sim, oracle, dtype):
+def test_summa_c_driver_on_a_1x1_grid_over_the_stand_in(sim, oracle, dtype, monkeypatch):
     """csrc/summa.cu compiled into the stand-in build: window packing (A dense, B panel-major), the k-panel schedule with
     ragged last panels, host and "device" operands, a host C swept in one pass or in two column halves, beta == 0 over a
     NaN C, k == 0, empty local pieces -- against the oracle (each panel is one simulated launch with beta = 1 after the
     first, so the comparison is by the k * eps bound).  Peers, flags and IPC are the multi-GPU runs' business."""
+    # read once by the stand-in build's driver, at its first call: a local C of >= 64 columns is swept in two halves
+    # (restored afterwards, so the real library in the same process keeps its default)
+    monkeypatch.setenv("B200_SUMMA_HOST_HALVES", "64")
     L = sim
     L.b200_summa_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.b200_summa_destroy.argtypes = [C.c_void_p]
