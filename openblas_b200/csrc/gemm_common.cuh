@@ -28,6 +28,9 @@ struct DeviceGemm {
    * the triangle and mask the stores of the tiles the diagonal crosses; the others answer
    * cudaErrorNotSupported and the caller falls back to block columns. */
   int tri = 0;
+  /* GEMM3M entry points (complex types): the dispatcher may compute the product from three real GEMMs
+   * (runtime.cu: gemm3m_on_device); 0 everywhere else */
+  int algo3m = 0;
 };
 
 /* triangle tests on a tile [m0, m0 + bm) x [n0, n0 + bn) and on an element */
@@ -131,6 +134,12 @@ cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const voi
                              double beta_im, void *c, int64_t ldc, cudaStream_t stream);
 
 cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cudaStream_t stream);
+/* GEMM3M (level3_aux.cu): the stored rows x cols complex matrix x -> three real planes of pitch ldp: re, sign * im and
+ * their sum (conj: sign = -1); and C := alpha * ((t1 - t2) + i (t3 - t1 - t2)) + beta * C from the three real products */
+cudaError_t launch_split3(int dtype, int64_t rows, int64_t cols, const void *x, int64_t ldx, int conj, void *re, void *im, void *sum,
+                          int64_t ldp, cudaStream_t stream);
+cudaError_t launch_combine3(int dtype, int64_t m, int64_t n, const void *t1, const void *t2, const void *t3, int64_t ldt, double alpha_re,
+                            double alpha_im, double beta_re, double beta_im, void *c, int64_t ldc, cudaStream_t stream);
 /* base case of the recursive TRMM / TRSM: one nb x nb (nb <= tri_block_max(dtype)) triangular block against nrhs vectors */
 int tri_block_max(int dtype);
 cudaError_t launch_tri_block(int dtype, int solve, int nb, int64_t nrhs, int eff_lower, int unit, int cj, const void *f, int64_t fs_i,

@@ -88,6 +88,7 @@ static blasint check_problem(const b200_problem *p, blasint ok_value) {
 B200_HIDDEN int b200_normalise(const call *in, b200_problem *out) {
   blasint info;
   out->dtype = in->dtype;
+  out->algo3m = in->name_idx != in->dtype;      /* the "CGEMM3M " / "ZGEMM3M " entry points */
   out->alpha = in->alpha;
   out->beta = in->beta;
   out->c = in->c;
@@ -155,9 +156,10 @@ CBLAS_REAL(cblas_dgemm, B200_D, double, double)
 CBLAS_REAL(cblas_sbgemm, B200_SB, bfloat16, float)
 CBLAS_CPLX(cblas_cgemm, B200_C, B200_C)
 CBLAS_CPLX(cblas_zgemm, B200_Z, B200_Z)
-/* GEMM3M: same contract as GEMM (the reference's generic targets forward it to GEMM too,
- * Changelog.txt:9-10); computed with the regular 4-multiply complex kernel, so the error
- * bound is the tighter GEMM one. */
+/* GEMM3M: same contract as GEMM.  Large products are computed from THREE real GEMMs (runtime.cu: gemm3m_on_device, the
+ * scheme of driver/level3/gemm3m_level3.c: 25 % fewer multiplications, error bound in terms of (|re| + |im|) sums);
+ * small ones with the regular 4-multiply complex kernel (the reference's generic targets forward GEMM3M to GEMM
+ * altogether, Changelog.txt:9-10). */
 CBLAS_CPLX(cblas_cgemm3m, B200_C, B200_C + NAME_3M_OFFSET)
 CBLAS_CPLX(cblas_zgemm3m, B200_Z, B200_Z + NAME_3M_OFFSET)
 

@@ -451,7 +451,88 @@ cudaError_t merge_t(int uplo, int herm, int64_t n, const void *t, int64_t ldt, d
   return cudaGetLastError();
 }
 
+/* ---- GEMM3M helpers: HBM-bound element-wise passes around three real GEMMs -------------------------------------
+ * split3: one read of the complex operand (16 / 8 bytes per element), three real planes written; combine3: three real
+ * planes read, C read only when beta != 0, C written.  O(mk + kn + mn) bytes against O(mnk) flops. */
+template <class R2, class R>
+__global__ void __launch_bounds__(256) split3_kernel(int64_t rows, int64_t cols, const R2 *__restrict__ x, int64_t ldx, R sign,
+                                                     R *__restrict__ xr, R *__restrict__ xi, R *__restrict__ xs, int64_t ldp) {
+  const int64_t tiles_r = (rows + 255) / 256;
+  for (int64_t t = blockIdx.x; t < tiles_r * cols; t += gridDim.x) {
+    const int64_t r = (t % tiles_r) * 256 + threadIdx.x, c = t / tiles_r;
+    if (r < rows) {
+      const R2 v = x[r + c * ldx];
+      const R im = sign * v.y;
+      xr[r + c * ldp] = v.x;
+      xi[r + c * ldp] = im;
+      xs[r + c * ldp] = v.x + im;
+    }
+  }
+}
+template <class R2, class R>
+__global__ void __launch_bounds__(256) combine3_kernel(int64_t m, int64_t n, const R *__restrict__ t1, const R *__restrict__ t2,
+                                                       const R *__restrict__ t3, int64_t ldt, R ar, R ai, R br, R bi, int use_beta,
+                                                       R2 *__restrict__ c, int64_t ldc) {
+  const int64_t tiles_r = (m + 255) / 256;
+  for (int64_t t = blockIdx.x; t < tiles_r * n; t += gridDim.x) {
+    const int64_t r = (t % tiles_r) * 256 + threadIdx.x, j = t / tiles_r;
+    if (r < m) {
+      const R a1 = t1[r + j * ldt], a2 = t2[r + j * ldt], a3 = t3[r + j * ldt];
+      const R pr = a1 - a2, pi = (a3 - a1) - a2;          /* Re = XrYr - XiYi,  Im = (Xr + Xi)(Yr + Yi) - XrYr - XiYi */
+      R2 o;
+      o.x = ar * pr - ai * pi;
+      o.y = ar * pi + ai * pr;
+      if (use_beta) {
+        const R2 old = c[r + j * ldc];
+        o.x += br * old.x - bi * old.y;
+        o.y += br * old.y + bi * old.x;
+      }
+      c[r + j * ldc] = o;
+    }
+  }
+}
+template <class R2, class R>
+cudaError_t split3_t(int64_t rows, int64_t cols, const void *x, int64_t ldx, int conj, void *re, void *im, void *sum, int64_t ldp,
+                     cudaStream_t s) {
+  int64_t blocks = ((rows + 255) / 256) * cols;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  split3_kernel<R2, R><<<(unsigned)blocks, 256, 0, s>>>(rows, cols, (const R2 *)x, ldx, conj ? (R)-1 : (R)1, (R *)re, (R *)im, (R *)sum, ldp);
+  return cudaGetLastError();
+}
+template <class R2, class R>
+cudaError_t combine3_t(int64_t m, int64_t n, const void *t1, const void *t2, const void *t3, int64_t ldt, double ar, double ai, double br,
+                       double bi, void *c, int64_t ldc, cudaStream_t s) {
+  int64_t blocks = ((m + 255) / 256) * n;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  combine3_kernel<R2, R><<<(unsigned)blocks, 256, 0, s>>>(m, n, (const R *)t1, (const R *)t2, (const R *)t3, ldt, (R)ar, (R)ai, (R)br, (R)bi,
+                                                          !(br == 0.0 && bi == 0.0), (R2 *)c, ldc);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t launch_split3(int dtype, int64_t rows, int64_t cols, const void *x, int64_t ldx, int conj, void *re, void *im, void *sum,
+                          int64_t ldp, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  cudaError_t e;
+  if (dtype == B200_C) e = split3_t<float2, float>(rows, cols, x, ldx, conj, re, im, sum, ldp, stream);
+  else if (dtype == B200_Z) e = split3_t<double2, double>(rows, cols, x, ldx, conj, re, im, sum, ldp, stream);
+  else return cudaErrorNotSupported;
+  if (e == cudaSuccess) count_launch("split3");
+  return e;
+}
+cudaError_t launch_combine3(int dtype, int64_t m, int64_t n, const void *t1, const void *t2, const void *t3, int64_t ldt, double alpha_re,
+                            double alpha_im, double beta_re, double beta_im, void *c, int64_t ldc, cudaStream_t stream) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  cudaError_t e;
+  if (dtype == B200_C) e = combine3_t<float2, float>(m, n, t1, t2, t3, ldt, alpha_re, alpha_im, beta_re, beta_im, c, ldc, stream);
+  else if (dtype == B200_Z) e = combine3_t<double2, double>(m, n, t1, t2, t3, ldt, alpha_re, alpha_im, beta_re, beta_im, c, ldc, stream);
+  else return cudaErrorNotSupported;
+  if (e == cudaSuccess) count_launch("combine3");
+  return e;
+}
 
 cudaError_t launch_expand_symmetric(int dtype, int uplo, int herm, int64_t n, const void *a, int64_t lda, void *out,
                                     int64_t ldo, cudaStream_t stream, int64_t i0, int64_t nr, int64_t j0, int64_t nc) {

@@ -233,9 +233,15 @@ static void read_scalars(const b200_problem *p, DeviceGemm &g) {
 
 /* Chooses the kernel family.  AUTO: the roofline kernels take every problem they support
  * above a small-size threshold; everything else goes to the generic kernel. */
+static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s);
+
 static cudaError_t dispatch(const DeviceGemm &g, cudaStream_t stream) {
   const bool product = g.k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
   if (!product && g.beta_re == 1.0 && g.beta_im == 0.0) return cudaSuccess; /* C unchanged */
+  if (g.algo3m && product && !g.tri) {
+    cudaError_t e3 = gemm3m_on_device(g, stream);
+    if (e3 != cudaErrorNotSupported) return e3;             /* too small, too big for the workspace, or not complex: 4 multiplies */
+  }
   int forced = g_forced_kernel.load(std::memory_order_relaxed);
   bool try_fast = product && forced != B200_K_GENERIC;
   if (forced == B200_K_AUTO) {
@@ -287,6 +293,68 @@ static PtrKind classify(const void *p) {
 }
 
 static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+/* ---- GEMM3M: three real products instead of four ------------------------------------------------------------------
+ * driver/level3/gemm3m_level3.c computes a complex product from three real ones over specially packed panels
+ * (kernel/generic/zgemm3m_*copy*.c add or subtract the real and imaginary parts while packing).  The same identity on
+ * whole matrices, with X = op(A), Y = op(B) (conjugation folded into the sign of the imaginary plane):
+ *     T1 = Xr Yr,  T2 = Xi Yi,  T3 = (Xr + Xi)(Yr + Yi);   Re(XY) = T1 - T2,  Im(XY) = T3 - T1 - T2.
+ * split3 writes the three real planes of each operand once (HBM-bound, O(mk + kn)), the three products are ordinary
+ * real GEMMs on the roofline kernels (op() becomes the real kernel's N / T), combine3 applies alpha and beta while it
+ * forms C.  6 mnk real flops instead of 8: ZGEMM3M 8192^3 in about 3/4 of ZGEMM's time.  Workspace (3 planes per
+ * operand and per product) comes from the stream-ordered pool; a product that would need more than
+ * B200_3M_WORKSPACE_LIMIT, or has an extent below B200_3M_MIN, stays on the 4-multiply kernel. */
+#ifdef B200_HOSTSIM
+#define B200_3M_MIN 8
+#else
+#define B200_3M_MIN 512
+#endif
+#define B200_3M_WORKSPACE_LIMIT ((size_t)24 << 30)
+static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s) {
+  if (g.dtype != B200_C && g.dtype != B200_Z) return cudaErrorNotSupported;
+  static const int64_t min_extent = getenv("B200_3M_MIN") ? atol(getenv("B200_3M_MIN")) : B200_3M_MIN;   /* 0 or less: never */
+  if (min_extent <= 0 || g.m < min_extent || g.n < min_extent || g.k < min_extent) return cudaErrorNotSupported;
+  const bool dbl = g.dtype == B200_Z;
+  const size_t rs = dbl ? 8 : 4;
+  const int64_t ra = (g.transa & 1) ? g.k : g.m, ca = (g.transa & 1) ? g.m : g.k;      /* A and B as stored */
+  const int64_t rb = (g.transb & 1) ? g.n : g.k, cb = (g.transb & 1) ? g.k : g.n;
+  auto pitch = [&](int64_t rows) { return (int64_t)(round_up((size_t)rows * rs, 128) / rs); };
+  const int64_t lpa = pitch(ra), lpb = pitch(rb), lpt = pitch(g.m);
+  const size_t plane_a = round_up((size_t)lpa * (size_t)ca * rs, 256), plane_b = round_up((size_t)lpb * (size_t)cb * rs, 256),
+               plane_t = round_up((size_t)lpt * (size_t)g.n * rs, 256);
+  const size_t total = 3 * (plane_a + plane_b + plane_t);
+  if (total > B200_3M_WORKSPACE_LIMIT) return cudaErrorNotSupported;
+#ifndef B200_HOSTSIM
+  /* keep up to 8 GiB of freed workspace in the stream-ordered pool between calls (by default the pool hands
+   * everything back at the next synchronisation and the next call maps it again); b200_shutdown trims it */
+  static std::once_flag pool_once;
+  std::call_once(pool_once, [] {
+    cudaMemPool_t pool; int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = (uint64_t)8 << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  });
+#endif
+  char *ws = nullptr;
+  if (cudaMallocAsync((void **)&ws, total, s) != cudaSuccess) { cudaGetLastError(); return cudaErrorNotSupported; }
+  char *pa[3], *pb[3], *pt[3];
+  for (int i = 0; i < 3; i++) { pa[i] = ws + i * plane_a; pb[i] = ws + 3 * plane_a + i * plane_b; pt[i] = ws + 3 * (plane_a + plane_b) + i * plane_t; }
+  cudaError_t e = launch_split3(g.dtype, ra, ca, g.a, g.lda, (g.transa & 2) != 0, pa[0], pa[1], pa[2], lpa, s);
+  if (e == cudaSuccess) e = launch_split3(g.dtype, rb, cb, g.b, g.ldb, (g.transb & 2) != 0, pb[0], pb[1], pb[2], lpb, s);
+  DeviceGemm r;
+  r.dtype = dbl ? B200_D : B200_S; r.transa = g.transa & 1; r.transb = g.transb & 1;
+  r.m = g.m; r.n = g.n; r.k = g.k; r.lda = lpa; r.ldb = lpb; r.ldc = lpt;
+  r.alpha_re = 1.0; r.alpha_im = 0.0; r.beta_re = 0.0; r.beta_im = 0.0;
+  for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+    r.a = pa[i]; r.b = pb[i]; r.c = pt[i];
+    e = dispatch(r, s);
+  }
+  if (e == cudaSuccess) e = launch_combine3(g.dtype, g.m, g.n, pt[0], pt[1], pt[2], lpt, g.alpha_re, g.alpha_im, g.beta_re, g.beta_im, g.c, g.ldc, s);
+  cudaFreeAsync(ws, s);
+  return e;
+}
 
 /* staged copy descriptor for one operand */
 struct Operand {
@@ -627,6 +695,7 @@ static int run_on_context(Context *ctx, const b200_problem *p) {
   DeviceGemm g;
   g.dtype = p->dtype; g.transa = p->transa; g.transb = p->transb;
   g.m = p->m; g.n = p->n; g.k = p->k;
+  g.algo3m = p->algo3m;
   read_scalars(p, g);
   const bool product = g.k > 0 && !(g.alpha_re == 0.0 && g.alpha_im == 0.0);
   const bool use_beta = !(g.beta_re == 0.0 && g.beta_im == 0.0);
@@ -1108,6 +1177,9 @@ static void shutdown_impl(void) {
   int cur = -1;
   const int dev = g_device.load(std::memory_order_acquire);
   if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) cudaSetDevice(dev); else cur = -1;
+#ifndef B200_HOSTSIM
+  { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); cudaGetLastError(); }
+#endif
   for (Context *c : ctxs) {
     scrub(c);
     if (c->dws) cudaFree(c->dws);

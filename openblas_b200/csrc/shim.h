@@ -30,6 +30,7 @@ typedef struct b200_problem {
   const void *a;
   const void *b;
   void *c;
+  int algo3m;           /* 1: called through a GEMM3M entry point (complex types): three real products may be used */
 } b200_problem;
 
 /* element size in bytes of A/B and of C for a dtype */

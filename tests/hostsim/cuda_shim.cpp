@@ -99,6 +99,8 @@ cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 
 /* what csrc/summa.cu needs beyond the above; a 1 x 1 grid never talks to a peer, so the IPC and driver entry points only
  * have to exist (they answer "not supported": the driver then takes its NCCL-synchronised branch, unused at world == 1) */
+cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }

@@ -194,6 +194,47 @@ cudaError_t launch_tri_merge(int dtype, int uplo, int herm, int64_t n, const voi
   count_launch("sim_tri_merge");
   return cudaSuccess;
 }
+/* GEMM3M helpers: the same element-wise arithmetic as level3_aux.cu's split3 / combine3 kernels */
+template <class R> void split3(int64_t rows, int64_t cols, const R *x, int64_t ldx, R sign, R *re, R *im, R *sum, int64_t ldp) {
+  for (int64_t c = 0; c < cols; c++)
+    for (int64_t r = 0; r < rows; r++) {
+      const R vr = x[2 * (r + c * ldx)], vi = sign * x[2 * (r + c * ldx) + 1];
+      re[r + c * ldp] = vr; im[r + c * ldp] = vi; sum[r + c * ldp] = vr + vi;
+    }
+}
+template <class R> void combine3(int64_t m, int64_t n, const R *t1, const R *t2, const R *t3, int64_t ldt, R ar, R ai, R br, R bi, bool use_beta,
+                                 R *c, int64_t ldc) {
+  for (int64_t j = 0; j < n; j++)
+    for (int64_t r = 0; r < m; r++) {
+      const R a1 = t1[r + j * ldt], a2 = t2[r + j * ldt], a3 = t3[r + j * ldt];
+      const R pr = a1 - a2, pi = (a3 - a1) - a2;
+      R ox = ar * pr - ai * pi, oy = ar * pi + ai * pr;
+      if (use_beta) {
+        const R cx = c[2 * (r + j * ldc)], cy = c[2 * (r + j * ldc) + 1];
+        ox += br * cx - bi * cy; oy += br * cy + bi * cx;
+      }
+      c[2 * (r + j * ldc)] = ox; c[2 * (r + j * ldc) + 1] = oy;
+    }
+}
+cudaError_t launch_split3(int dtype, int64_t rows, int64_t cols, const void *x, int64_t ldx, int conj, void *re, void *im, void *sum, int64_t ldp,
+                          cudaStream_t) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if (dtype == B200_C) split3<float>(rows, cols, (const float *)x, ldx, conj ? -1.f : 1.f, (float *)re, (float *)im, (float *)sum, ldp);
+  else if (dtype == B200_Z) split3<double>(rows, cols, (const double *)x, ldx, conj ? -1.0 : 1.0, (double *)re, (double *)im, (double *)sum, ldp);
+  else return cudaErrorNotSupported;
+  count_launch("sim_split3");
+  return cudaSuccess;
+}
+cudaError_t launch_combine3(int dtype, int64_t m, int64_t n, const void *t1, const void *t2, const void *t3, int64_t ldt, double ar, double ai,
+                            double br, double bi, void *c, int64_t ldc, cudaStream_t) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  const bool use_beta = !(br == 0.0 && bi == 0.0);
+  if (dtype == B200_C) combine3<float>(m, n, (const float *)t1, (const float *)t2, (const float *)t3, ldt, (float)ar, (float)ai, (float)br, (float)bi, use_beta, (float *)c, ldc);
+  else if (dtype == B200_Z) combine3<double>(m, n, (const double *)t1, (const double *)t2, (const double *)t3, ldt, ar, ai, br, bi, use_beta, (double *)c, ldc);
+  else return cudaErrorNotSupported;
+  count_launch("sim_combine3");
+  return cudaSuccess;
+}
 cudaError_t launch_real_diagonal(int dtype, int64_t n, void *c, int64_t ldc, cudaStream_t) {
   if (dtype == B200_C) for (int64_t i = 0; i < n; i++) ((float *)c)[2 * (i + i * ldc) + 1] = 0.f;
   if (dtype == B200_Z) for (int64_t i = 0; i < n; i++) ((double *)c)[2 * (i + i * ldc) + 1] = 0.0;

@@ -451,3 +451,57 @@ def test_midsize_pageable_host_operands(ob, oracle):
         got = c0.copy()
         run_cblas(ob, cpu.D, ob.cblas.ColMajor, ta, tb, m, n, k, 0.7, a, lda, b, ldb, 1.3, got, ldc)
         check(oracle, cpu.D, ta, tb, m, n, k, 0.7, a, lda, b, ldb, 1.3, c0, ldc, got, "pageable-mid")
+
+
+@pytest.mark.parametrize("dtype", [cpu.Z, cpu.CX])
+def test_gemm3m_large_products_use_three_real_gemms(ob, oracle, dtype):
+    """?gemm3m with every extent >= 512: split3 of both operands, three REAL GEMMs on the roofline kernels, combine3
+    (runtime.cu: gemm3m_on_device).  Op pairs that cover N / T / R / C on each side, beta != 0 and beta == 0 over a NaN
+    C, device and pageable host operands.  Judged like the reference's 3M acceptance driver (ctest/c_zblat3c_3m.c:
+    err / (eps * gauge) < 16 with gauge = |alpha| sum (|re| + |im|)(|re| + |im|) + |beta| (|re| + |im|) of C), against a
+    complex128 product; 2 + 3 + 1 launches; the plain ?gemm entry point keeps the 4-multiply kernel."""
+    import ctypes as C
+    import torch
+    lib = ob.lib()
+    rng = np.random.default_rng(3300 + dtype)
+    eps = 2.0 ** -52 if dtype == cpu.Z else 2.0 ** -23
+    ct = np.complex128 if dtype == cpu.Z else np.complex64
+    name = "cblas_" + cpu.DTYPE_NAMES[dtype] + "gemm3m"
+    m, n, k = 640, 768, 512
+    abs1 = lambda z: np.abs(z.real) + np.abs(z.imag)
+    for ta, tb, where in ((0, 0, "device"), (1, 2, "device"), (3, 1, "host"), (2, 3, "device")):
+        ra, ca = (k, m) if ta & 1 else (m, k)
+        rb, cb = (n, k) if tb & 1 else (k, n)
+        lda, ldb, ldc = ra + 8, rb + 4, m + 6
+        a = ((rng.random((ca, lda)) - 0.5) + 1j * (rng.random((ca, lda)) - 0.5)).astype(ct)
+        b = ((rng.random((cb, ldb)) - 0.5) + 1j * (rng.random((cb, ldb)) - 0.5)).astype(ct)
+        c0 = ((rng.random((n, ldc)) - 0.5) + 1j * (rng.random((n, ldc)) - 0.5)).astype(ct)
+        # numpy holds the column-major matrices transposed: element (i, j) is x[j, i]
+        opx = lambda x, rows, t: {0: x[:, :rows].T, 1: x[:, :rows], 2: x[:, :rows].T.conj(), 3: x[:, :rows].conj()}[t]
+        X, Y = opx(a.astype(np.complex128), ra, ta), opx(b.astype(np.complex128), rb, tb)          # m x k, k x n
+        for alpha, beta in ((0.7 - 0.9j, 1.3 - 1.1j), (1.0 + 0.0j, 0.0j)):
+            ref = alpha * (X @ Y) + beta * c0[:, :m].T.astype(np.complex128)
+            gauge = abs1(np.complex128(alpha)) * (abs1(X) @ abs1(Y)) + abs1(np.complex128(beta)) * abs1(c0[:, :m].T.astype(np.complex128))
+            start = c0.copy()
+            if beta == 0:
+                start[:, :m] = np.nan
+            al, be = np.array([alpha], dtype=ct), np.array([beta], dtype=ct)
+            before = ob.cblas.launch_count()
+            if where == "device":
+                da, db, dc = (torch.from_numpy(np.ascontiguousarray(x).view(np.float64 if dtype == cpu.Z else np.float32)).cuda() for x in (a, b, start))
+                getattr(lib, name)(102, cpu.CBLAS_TRANS[ta], cpu.CBLAS_TRANS[tb], m, n, k, C.c_void_p(al.ctypes.data), C.c_void_p(da.data_ptr()), lda,
+                                   C.c_void_p(db.data_ptr()), ldb, C.c_void_p(be.ctypes.data), C.c_void_p(dc.data_ptr()), ldc)
+                got = dc.cpu().numpy().view(ct).reshape(start.shape)
+            else:
+                got = start.copy()
+                getattr(lib, name)(102, cpu.CBLAS_TRANS[ta], cpu.CBLAS_TRANS[tb], m, n, k, C.c_void_p(al.ctypes.data), C.c_void_p(a.ctypes.data), lda,
+                                   C.c_void_p(b.ctypes.data), ldb, C.c_void_p(be.ctypes.data), C.c_void_p(got.ctypes.data), ldc)
+            assert ob.cblas.last_kernel() == "combine3", ob.cblas.last_kernel()
+            assert ob.cblas.launch_count() - before == 6
+            ratio = (abs1(got[:, :m].T.astype(np.complex128) - ref) / (eps * gauge)).max()
+            assert ratio < 16.0, (ta, tb, where, alpha, ratio)
+            assert np.array_equal(got[:, m:].view(np.uint8), start[:, m:].view(np.uint8)), "padding rows changed"
+    # the plain entry point is untouched by all this
+    a2, b2, c2 = ((rng.random((k, m)) - 0.5) + 0j).astype(ct), ((rng.random((n, k)) - 0.5) + 0j).astype(ct), np.zeros((n, m), dtype=ct)
+    run_cblas(ob, dtype, ob.cblas.ColMajor, 0, 0, m, n, k, 1.0, a2, m, b2, k, 0.0, c2, m)
+    assert ob.cblas.last_kernel() != "combine3"

@@ -728,3 +728,59 @@ def L_operand(rng, t, cplx, cols, ld):
     if cplx:
         x = x + 1j * (rng.random((cols, ld)) - 0.5)
     return x.astype(t)
+
+
+@pytest.mark.parametrize("dtype", [cpu.Z, cpu.CX])
+def test_gemm3m_runs_three_real_products(sim, oracle, dtype):
+    """?gemm3m_ above the size limit (8 in this build, 512 in the product): split3 of both operands, three REAL GEMMs,
+    combine3 -- for every op pair (conjugation = sign of the imaginary plane, transposition = the real GEMM's own),
+    ragged shapes, beta == 0 over a NaN C, host and "device" operands; accepted the way the reference's 3M ctest driver
+    accepts it (ctest/c_zblat3c_3m.c: err / (eps * gauge) < 16 with the |re| + |im| gauge).  Below the limit, and through
+    the plain ?gemm_ entry points, nothing changes."""
+    sim.b200_last_kernel.restype = C.c_char_p
+    rng = np.random.default_rng(1200 + dtype)
+    name = cpu.DTYPE_NAMES[dtype] + "gemm3m_"
+    i = lambda v: C.byref(C.c_int(int(v)))
+    P = lambda x: C.c_void_p(x) if isinstance(x, int) else x.ctypes.data_as(C.c_void_p)
+
+    def gemm3m(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        al, be = cpu.scalar_bytes(dtype, alpha), cpu.scalar_bytes(dtype, beta)
+        getattr(sim, name)(C.c_char_p(cpu.TRANS_CHAR[ta].encode()), C.c_char_p(cpu.TRANS_CHAR[tb].encode()), i(m), i(n), i(k), cpu._ptr(al), P(a), i(lda),
+                           P(b), i(ldb), cpu._ptr(be), P(c), i(ldc))
+
+    for (m, n, k) in ((40, 33, 29), (9, 64, 8), (17, 8, 50)):
+        for ta in range(4):
+            for tb in range(4):
+                a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(3, 2, 5))
+                for alpha, beta in ((0.7 - 0.9j, 1.3 - 1.1j), (1.0, 0.0)):
+                    start = c0.copy()
+                    if beta == 0.0:
+                        start[:, :m] = np.nan
+                    got = start.copy()
+                    before = sim.b200_launch_count()
+                    if (ta + tb) % 2 == 0:
+                        gemm3m(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, got, ldc)
+                    else:
+                        bufs = []
+                        for arr in (a, b, start):
+                            p = sim.hostsim_device_alloc(arr.nbytes)
+                            C.memmove(p, arr.ctypes.data, arr.nbytes)
+                            bufs.append(p)
+                        gemm3m(ta, tb, m, n, k, alpha, bufs[0], lda, bufs[1], ldb, beta, bufs[2], ldc)
+                        C.memmove(got.ctypes.data, bufs[2], got.nbytes)
+                        for p in bufs:
+                            sim.hostsim_free(p)
+                    assert sim.b200_launch_count() - before == 6 and sim.b200_last_kernel() == b"sim_combine3"
+                    assert oracle.mmch(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, got, ldc) < 16.0, (m, n, k, ta, tb, alpha)
+                    assert np.array_equal(got[:, m:].view(np.uint8), start[:, m:].view(np.uint8))      # padding rows keep their bytes
+    # below the limit: the 4-multiply kernel, bit for bit the GEMM result; and ?gemm_ itself never takes the 3M path
+    a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 0, 3, 7, 30, 30, pad=(1, 1, 1))
+    got, want = c0.copy(), c0.copy()
+    gemm3m(0, 3, 7, 30, 30, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, got, ldc)
+    assert sim.b200_last_kernel() != b"sim_combine3"
+    fgemm(sim, dtype, 0, 3, 7, 30, 30, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, want, ldc)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 1, 0, 40, 33, 29, pad=(1, 1, 1))
+    got = c0.copy()
+    fgemm(sim, dtype, 1, 0, 40, 33, 29, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, got, ldc)
+    assert sim.b200_last_kernel() != b"sim_combine3"
