@@ -675,7 +675,38 @@ def run_extras(ob, torch, dev, stream, args):
     fam["sbgemmt"] = sbgemmt_row(torch, ob, dev, 8192)
     fam["note"] = "n = k = 8192, device-resident operands, wall time of the synchronous Fortran-ABI calls (3 after a warm-up); flops as a GEMM of the same useful work"
     out["level3_8192"] = fam
+    # (f) SURVEY 8 f1: ?GEMM3M on three real products against ?GEMM, 8192^3 NN, device operands (guarded: a failure here
+    # must not cost the line its headline)
+    try:
+        out["gemm3m_8192"] = gemm3m_rows(torch, ob, dev, 8192)
+    except Exception as exc:       # noqa: BLE001
+        out["gemm3m_8192"] = {"error": repr(exc)}
     return out
+
+
+def gemm3m_rows(torch, ob, dev, n):
+    import ctypes as C
+    lib = ob.lib()
+    i_ = lambda v: C.byref(C.c_int(int(v)))
+    res = {"note": "wall time of the synchronous Fortran-ABI calls (3 after two warm-ups); TFLOP/s in ZGEMM's 8mnk count for both"}
+    for dtype, rdt, ct in (("z", torch.float64, C.c_double), ("c", torch.float32, C.c_float)):
+        a, b, c = (torch.rand((n, n, 2), device=dev, dtype=rdt) - 0.5 for _ in range(3))
+        al, be = (ct * 2)(0.7, -0.9), (ct * 2)(0.0, 0.0)
+        row = {}
+        for name in ("gemm_", "gemm3m_"):
+            f = lambda: getattr(lib, dtype + name)(C.c_char_p(b"N"), C.c_char_p(b"N"), i_(n), i_(n), i_(n), al, C.c_void_p(a.data_ptr()), i_(n),
+                                                   C.c_void_p(b.data_ptr()), i_(n), be, C.c_void_p(c.data_ptr()), i_(n))
+            f(); f(); torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                f()
+            ms = (time.perf_counter() - t0) / 3 * 1e3
+            row[name + "ms"], row[name + "tflops_8mnk"], row[name + "kernel"] = ms, 8.0 * n ** 3 / (ms * 1e-3) / 1e12, ob.cblas.last_kernel()
+        row["speedup"] = row["gemm_ms"] / row["gemm3m_ms"]
+        res[dtype] = row
+        del a, b, c
+        torch.cuda.empty_cache()
+    return res
 
 
 def run_e2e(ob, torch, code, dtype, m, n, k, tdt, odt, args):
