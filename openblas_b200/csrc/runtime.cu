@@ -316,6 +316,9 @@ static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s) {
   if (min_extent <= 0 || g.m < min_extent || g.n < min_extent || g.k < min_extent) return cudaErrorNotSupported;
   const bool dbl = g.dtype == B200_Z;
   const size_t rs = dbl ? 8 : 4;
+  /* split3 / combine3 read and write whole (re, im) pairs: operands that are only aligned to their real type take the
+   * 4-multiply path, which has its own rules for them */
+  if ((((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & (2 * rs - 1)) != 0) return cudaErrorNotSupported;
   const int64_t ra = (g.transa & 1) ? g.k : g.m, ca = (g.transa & 1) ? g.m : g.k;      /* A and B as stored */
   const int64_t rb = (g.transb & 1) ? g.n : g.k, cb = (g.transb & 1) ? g.k : g.n;
   auto pitch = [&](int64_t rows) { return (int64_t)(round_up((size_t)rows * rs, 128) / rs); };
