@@ -302,14 +302,20 @@ static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
  * split3 writes the three real planes of each operand once (HBM-bound, O(mk + kn)), the three products are ordinary
  * real GEMMs on the roofline kernels (op() becomes the real kernel's N / T), combine3 applies alpha and beta while it
  * forms C.  6 mnk real flops instead of 8: ZGEMM3M 8192^3 in about 3/4 of ZGEMM's time.  Workspace (3 planes per
- * operand and per product) comes from the stream-ordered pool; a product that would need more than
- * B200_3M_WORKSPACE_LIMIT, or has an extent below B200_3M_MIN, stays on the 4-multiply kernel. */
+ * operand and per product) comes from the stream-ordered pool; when the whole product would need more than
+ * B200_3M_WORKSPACE_LIMIT, k is cut into chunks; a product whose C planes alone exceed the limit, or with an extent below
+ * B200_3M_MIN, stays on the 4-multiply kernel. */
 #ifdef B200_HOSTSIM
 #define B200_3M_MIN 8
 #else
 #define B200_3M_MIN 512
 #endif
 #define B200_3M_WORKSPACE_LIMIT ((size_t)24 << 30)
+#ifdef B200_HOSTSIM
+#define B200_3M_CHUNK_MIN 8
+#else
+#define B200_3M_CHUNK_MIN 1024
+#endif
 static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s) {
   if (g.dtype != B200_C && g.dtype != B200_Z) return cudaErrorNotSupported;
   static const int64_t min_extent = getenv("B200_3M_MIN") ? atol(getenv("B200_3M_MIN")) : B200_3M_MIN;   /* 0 or less: never */
@@ -319,14 +325,25 @@ static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s) {
   /* split3 / combine3 read and write whole (re, im) pairs: operands that are only aligned to their real type take the
    * 4-multiply path, which has its own rules for them */
   if ((((uintptr_t)g.a | (uintptr_t)g.b | (uintptr_t)g.c) & (2 * rs - 1)) != 0) return cudaErrorNotSupported;
-  const int64_t ra = (g.transa & 1) ? g.k : g.m, ca = (g.transa & 1) ? g.m : g.k;      /* A and B as stored */
-  const int64_t rb = (g.transb & 1) ? g.n : g.k, cb = (g.transb & 1) ? g.k : g.n;
+  /* k goes through in chunks of kc -- all of it when the workspace allows, else halved until it does (the tall-skinny
+   * 65536 x 256 x 65536 shape needs 100 GB of planes in one piece, 13 GB in chunks of 8192): each chunk is split,
+   * multiplied and combined into C, the first with the caller's beta, the others with beta = 1 */
+  const char *lim_env = getenv("B200_3M_WORKSPACE_BYTES");
+  const size_t limit = lim_env ? (size_t)atoll(lim_env) : B200_3M_WORKSPACE_LIMIT;
   auto pitch = [&](int64_t rows) { return (int64_t)(round_up((size_t)rows * rs, 128) / rs); };
-  const int64_t lpa = pitch(ra), lpb = pitch(rb), lpt = pitch(g.m);
-  const size_t plane_a = round_up((size_t)lpa * (size_t)ca * rs, 256), plane_b = round_up((size_t)lpb * (size_t)cb * rs, 256),
-               plane_t = round_up((size_t)lpt * (size_t)g.n * rs, 256);
-  const size_t total = 3 * (plane_a + plane_b + plane_t);
-  if (total > B200_3M_WORKSPACE_LIMIT) return cudaErrorNotSupported;
+  const int64_t lpt = pitch(g.m);
+  const size_t plane_t = round_up((size_t)lpt * (size_t)g.n * rs, 256);
+  int64_t kc = g.k, lpa = 0, lpb = 0;
+  size_t plane_a = 0, plane_b = 0, total = 0;
+  for (;;) {
+    lpa = pitch((g.transa & 1) ? kc : g.m); lpb = pitch((g.transb & 1) ? g.n : kc);
+    plane_a = round_up((size_t)lpa * (size_t)((g.transa & 1) ? g.m : kc) * rs, 256);
+    plane_b = round_up((size_t)lpb * (size_t)((g.transb & 1) ? kc : g.n) * rs, 256);
+    total = 3 * (plane_a + plane_b + plane_t);
+    if (total <= limit) break;
+    if (kc <= B200_3M_CHUNK_MIN) return cudaErrorNotSupported;
+    kc = ((kc / 2 + B200_3M_CHUNK_MIN - 1) / B200_3M_CHUNK_MIN) * B200_3M_CHUNK_MIN;
+  }
 #ifndef B200_HOSTSIM
   /* keep up to 8 GiB of freed workspace in the stream-ordered pool between calls (by default the pool hands
    * everything back at the next synchronisation and the next call maps it again); b200_shutdown trims it */
@@ -344,17 +361,27 @@ static cudaError_t gemm3m_on_device(const DeviceGemm &g, cudaStream_t s) {
   if (cudaMallocAsync((void **)&ws, total, s) != cudaSuccess) { cudaGetLastError(); return cudaErrorNotSupported; }
   char *pa[3], *pb[3], *pt[3];
   for (int i = 0; i < 3; i++) { pa[i] = ws + i * plane_a; pb[i] = ws + 3 * plane_a + i * plane_b; pt[i] = ws + 3 * (plane_a + plane_b) + i * plane_t; }
-  cudaError_t e = launch_split3(g.dtype, ra, ca, g.a, g.lda, (g.transa & 2) != 0, pa[0], pa[1], pa[2], lpa, s);
-  if (e == cudaSuccess) e = launch_split3(g.dtype, rb, cb, g.b, g.ldb, (g.transb & 2) != 0, pb[0], pb[1], pb[2], lpb, s);
+  const size_t es = 2 * rs;
+  cudaError_t e = cudaSuccess;
   DeviceGemm r;
   r.dtype = dbl ? B200_D : B200_S; r.transa = g.transa & 1; r.transb = g.transb & 1;
-  r.m = g.m; r.n = g.n; r.k = g.k; r.lda = lpa; r.ldb = lpb; r.ldc = lpt;
+  r.m = g.m; r.n = g.n; r.lda = lpa; r.ldb = lpb; r.ldc = lpt;
   r.alpha_re = 1.0; r.alpha_im = 0.0; r.beta_re = 0.0; r.beta_im = 0.0;
-  for (int i = 0; i < 3 && e == cudaSuccess; i++) {
-    r.a = pa[i]; r.b = pb[i]; r.c = pt[i];
-    e = dispatch(r, s);
+  for (int64_t k0 = 0; k0 < g.k && e == cudaSuccess; k0 += kc) {
+    const int64_t kk = g.k - k0 < kc ? g.k - k0 : kc;
+    /* columns k0.. of a stored m x k operand, rows k0.. of a stored k x m one */
+    const char *a0 = (const char *)g.a + ((g.transa & 1) ? (size_t)k0 : (size_t)k0 * (size_t)g.lda) * es;
+    const char *b0 = (const char *)g.b + ((g.transb & 1) ? (size_t)k0 * (size_t)g.ldb : (size_t)k0) * es;
+    e = launch_split3(g.dtype, (g.transa & 1) ? kk : g.m, (g.transa & 1) ? g.m : kk, a0, g.lda, (g.transa & 2) != 0, pa[0], pa[1], pa[2], lpa, s);
+    if (e == cudaSuccess) e = launch_split3(g.dtype, (g.transb & 1) ? g.n : kk, (g.transb & 1) ? kk : g.n, b0, g.ldb, (g.transb & 2) != 0, pb[0], pb[1], pb[2], lpb, s);
+    r.k = kk;
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+      r.a = pa[i]; r.b = pb[i]; r.c = pt[i];
+      e = dispatch(r, s);
+    }
+    if (e == cudaSuccess)
+      e = launch_combine3(g.dtype, g.m, g.n, pt[0], pt[1], pt[2], lpt, g.alpha_re, g.alpha_im, k0 == 0 ? g.beta_re : 1.0, k0 == 0 ? g.beta_im : 0.0, g.c, g.ldc, s);
   }
-  if (e == cudaSuccess) e = launch_combine3(g.dtype, g.m, g.n, pt[0], pt[1], pt[2], lpt, g.alpha_re, g.alpha_im, g.beta_re, g.beta_im, g.c, g.ldc, s);
   cudaFreeAsync(ws, s);
   return e;
 }

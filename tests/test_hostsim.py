@@ -731,7 +731,7 @@ def L_operand(rng, t, cplx, cols, ld):
 
 
 @pytest.mark.parametrize("dtype", [cpu.Z, cpu.CX])
-def test_gemm3m_runs_three_real_products(sim, oracle, dtype):
+def test_gemm3m_runs_three_real_products(sim, oracle, dtype, monkeypatch):
     """?gemm3m_ above the size limit (8 in this build, 512 in the product): split3 of both operands, three REAL GEMMs,
     combine3 -- for every op pair (conjugation = sign of the imaginary plane, transposition = the real GEMM's own),
     ragged shapes, beta == 0 over a NaN C, host and "device" operands; accepted the way the reference's 3M ctest driver
@@ -773,6 +773,33 @@ def test_gemm3m_runs_three_real_products(sim, oracle, dtype):
                     assert sim.b200_launch_count() - before == 6 and sim.b200_last_kernel() == b"sim_combine3"
                     assert oracle.mmch(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c0, ldc, got, ldc) < 16.0, (m, n, k, ta, tb, alpha)
                     assert np.array_equal(got[:, m:].view(np.uint8), start[:, m:].view(np.uint8))      # padding rows keep their bytes
+    # a workspace limit that does not hold the whole product: k goes through in chunks (first chunk with the caller's
+    # beta, the others accumulate), every op pair; a limit below the C planes alone: the 4-multiply kernel
+    m, n, k = 40, 33, 29
+    rs = 8 if dtype == cpu.Z else 4
+    pitch = lambda rows: -(-rows * rs // 128) * 128                      # bytes per plane column, as in gemm3m_on_device
+    plane = lambda rows, cols: -(-pitch(rows) * cols // 256) * 256
+    chunked = 0
+    for ta in range(4):
+        for tb in range(4):
+            a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, ta, tb, m, n, k, pad=(2, 3, 1))
+            need = lambda kc: 3 * ((plane(kc, m) if ta & 1 else plane(m, kc)) + (plane(n, kc) if tb & 1 else plane(kc, n)) + plane(m, n))
+            monkeypatch.setenv("B200_3M_WORKSPACE_BYTES", str(need(8)))       # chunks of 8 always fit; whether 16 or all 29 do depends on the pitch rounding
+            got = c0.copy()
+            before = sim.b200_launch_count()
+            gemm3m(ta, tb, m, n, k, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, got, ldc)
+            launches = sim.b200_launch_count() - before
+            assert sim.b200_last_kernel() == b"sim_combine3" and launches % 6 == 0, (ta, tb, launches)
+            expect = 1 if need(29) <= need(8) else (2 if need(16) <= need(8) else 4)
+            assert launches // 6 == expect, (ta, tb, launches, expect)
+            chunked += launches // 6 > 1
+            assert oracle.mmch(dtype, ta, tb, m, n, k, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, c0, ldc, got, ldc) < 16.0, (ta, tb, "chunked")
+    assert chunked >= 8
+    monkeypatch.setenv("B200_3M_WORKSPACE_BYTES", "1000")
+    got = c0.copy()
+    gemm3m(3, 3, m, n, k, 0.7 - 0.9j, a, lda, b, ldb, 1.3 - 1.1j, got, ldc)
+    assert sim.b200_last_kernel() != b"sim_combine3"
+    monkeypatch.delenv("B200_3M_WORKSPACE_BYTES")
     # below the limit: the 4-multiply kernel, bit for bit the GEMM result; and ?gemm_ itself never takes the 3M path
     a, lda, b, ldb, c0, ldc = problem(rng, oracle, dtype, 0, 3, 7, 30, 30, pad=(1, 1, 1))
     got, want = c0.copy(), c0.copy()
