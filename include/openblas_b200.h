@@ -65,7 +65,9 @@ void cblas_sbgemm(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLA
                   blasint M, blasint N, blasint K, float alpha, const bfloat16 *A, blasint lda,
                   const bfloat16 *B, blasint ldb, float beta, float *C, blasint ldc);
 
-/* ---- CBLAS GEMM3M (cblas.h:304-309; interface/gemm.c built with -DGEMM3M) ----------- */
+/* ---- CBLAS GEMM3M (cblas.h:304-309; interface/gemm.c built with -DGEMM3M; driver/level3/gemm3m_level3.c):
+ *      every extent >= 512 (B200_3M_MIN): three real GEMMs, error bound in (|re| + |im|) gauges as ctest's 3M
+ *      driver checks it; smaller products: the 4-multiply kernel ---------------------------------------------- */
 void cblas_cgemm3m(enum CBLAS_ORDER Order, enum CBLAS_TRANSPOSE TransA, enum CBLAS_TRANSPOSE TransB,
                    blasint M, blasint N, blasint K, const void *alpha, const void *A, blasint lda,
                    const void *B, blasint ldb, const void *beta, void *C, blasint ldc);

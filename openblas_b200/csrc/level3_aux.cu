@@ -1,7 +1,7 @@
 /*
- * level3_aux.cu -- the helper kernels behind the rest of level 3 (runtime_level3.inl): three HBM-bound
- * passes (expand_symmetric, tri_merge, real_diagonal) and the 64 x 64 triangular block kernel of
- * TRMM / TRSM (tri_block_kernel, described where it is defined).  The first two are plain coalesced
+ * level3_aux.cu -- the helper kernels behind the rest of level 3 (runtime_level3.inl) and GEMM3M: HBM-bound
+ * passes (expand_symmetric, tri_merge, real_diagonal, split3, combine3) and the triangular block kernels of
+ * TRMM / TRSM (tri_block_kernel, tri_block_reg_kernel, described where they are defined).  The first two are plain coalesced
  * passes over an n x n matrix: 32 x 8 thread
  * blocks walk columns (the contiguous direction of column-major storage) so every warp reads and
  * writes 128 / 256 / 512 contiguous bytes; the grid is sized to the matrix, capped at a multiple
@@ -15,6 +15,8 @@
  *     (driver/level3/syrk_kernel.c writes only the triangle part of a diagonal block through
  *     a scratch tile; syrk_k.c's syrk_beta scales only the triangle); Hermitian flavour zeroes
  *     the diagonal's imaginary part (zherk_kernel.c, zherk_beta.c).  T == nullptr means "0".
+ *   split3 / combine3: the element-wise passes around the three real products of GEMM3M (runtime.cu:
+ *     gemm3m_on_device; what kernel/generic/zgemm3m_ncopy_*.c / zgemm3m_tcopy_*.c do while packing in the reference).
  */
 #include <cstdlib>
 #include <cstring>
